@@ -1,0 +1,174 @@
+/*
+ * swmhd.h — C ABI of libswmhd_cuda.so: the B200 (sm_100a) replacement for the
+ * per-RK3-substage hot path of writingindy/SWMHD.
+ *
+ * The reference has no FFI of its own.  Its only extension point is the Julia
+ * closure contract  Forcing(f, discrete_form=true)  with
+ *     f(i, j, k, grid, clock, model_fields)::Float64
+ * (jacobian_formulation/SWMHD_example.jl:30-31,
+ *  jacobian_formulation/sw_mhd_jacobian_functions.jl:20-26,
+ *  divergence_formulation/divergence_sw_mhd.jl:28-29,
+ *  divergence_formulation/sw_mhd_divergence_functions.jl:162-170),
+ * which Oceananigans inlines into its tendency kernels.  A per-cell callback
+ * cannot cross a C ABI at speed, so the boundary sits one level up, at
+ * time_step!(model, dt): every entry point below replaces one call the
+ * reference scripts make (directly or through Simulation/run!) on a
+ * ShallowWaterModel.  INTEGRATION.md shows the Julia `ccall` stubs.
+ *
+ * Memory contract: every host buffer passed to set/get is the *parent array*
+ * of an Oceananigans Field: (Nx+2Hx) x (Ny_f+2Hy) doubles, column-major,
+ * i fastest, Hx=Hy=3.  Ny_f = Ny, except Ny+1 for the y-face field (v|vh)
+ * when topo_y is Bounded.  0-based offset of logical (i,j), 1-based interior:
+ *     (i + Hx - 1) + (Nx + 2Hx) * (j + Hy - 1)
+ *
+ * All functions return SWMHD_OK (0) or a negative error code; no exceptions
+ * and no callbacks cross the ABI.  A context is not re-entrant.
+ * There is NO CPU fallback: without a usable CUDA device swmhd_create fails.
+ */
+#ifndef SWMHD_ABI_H_
+#define SWMHD_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWMHD_ABI_VERSION 1
+
+enum {
+    SWMHD_OK              =  0,
+    SWMHD_ERR_ARG         = -1,  /* bad argument / unsupported option        */
+    SWMHD_ERR_CUDA        = -2,  /* CUDA runtime error (see swmhd_last_error) */
+    SWMHD_ERR_NONFINITE   = -3,  /* state contains NaN/Inf                    */
+    SWMHD_ERR_NODEVICE    = -4,  /* no CUDA device: there is no CPU fallback  */
+    SWMHD_ERR_STATE       = -5   /* call sequence error                       */
+};
+
+enum { SWMHD_PERIODIC = 0, SWMHD_BOUNDED = 1 };
+
+/* formulation = which of the reference's two model set-ups is being run */
+enum {
+    SWMHD_JACOBIAN   = 0, /* VectorInvariantFormulation + lorentz_force_func_x/y
+                             (SWMHD_example.jl:21-33)                          */
+    SWMHD_DIVERGENCE = 1  /* ConservativeFormulation + div_lorentz_x/y
+                             (divergence_sw_mhd.jl:19-31)                      */
+};
+
+/* field ids: solution (u|uh, v|vh, h) followed by the tracer A */
+enum { SWMHD_U = 0, SWMHD_V = 1, SWMHD_H = 2, SWMHD_A = 3, SWMHD_NFIELDS = 4 };
+
+/* arithmetic mode of the CUDA kernels */
+enum {
+    SWMHD_ARITH_FAST   = 0, /* FMA contraction, fused-division WENO weights:
+                               <=1e-12 rel-L2 per step vs the strict form    */
+    SWMHD_ARITH_STRICT = 1  /* no contraction, IEEE division, operation order
+                               of the spec: bit-identical to oracle/         */
+};
+
+/* Ambiguity-register switches. Zero = default. */
+enum {
+    SWMHD_FLAG_WENO_JS        = 1 << 0, /* C1: JS weights instead of Z        */
+    SWMHD_FLAG_PRESSURE_GHDH  = 1 << 1, /* C5: g*Ix(h)*dx(h) not dx(g h^2/2)  */
+    SWMHD_FLAG_CDIVU_OVER_H   = 1 << 2, /* C6: A*div(uh,vh)/h                 */
+    SWMHD_FLAG_DIAG_CENTRED   = 1 << 3  /* C11: centre-averaged squares       */
+};
+
+typedef struct swmhd_config {
+    int32_t abi_version;   /* SWMHD_ABI_VERSION                               */
+    int32_t Nx, Ny;        /* global interior size                            */
+    int32_t Hx, Hy;        /* must be 3, 3 (WENO5 default halo)               */
+    int32_t topo_x, topo_y;/* SWMHD_PERIODIC | SWMHD_BOUNDED (x: periodic only)*/
+    int32_t formulation;   /* SWMHD_JACOBIAN | SWMHD_DIVERGENCE               */
+    int32_t arith;         /* SWMHD_ARITH_FAST | SWMHD_ARITH_STRICT           */
+    int32_t flags;         /* SWMHD_FLAG_*                                    */
+    double  dx, dy;        /* Lx/Nx, Ly/Ny                                    */
+    double  g, f;          /* gravitational_acceleration, FPlane f            */
+    double  weno_eps;      /* C2: 1e-6                                        */
+    double  h_ref;         /* h_i in the potential-energy diagnostic (1.0)    */
+    /* GradientBoundaryCondition on A at south/north (Bounded-y only),
+       SWMHD_example.jl:19 / divergence_sw_mhd.jl:17 (commented in both)     */
+    int32_t A_gradient_bc; /* 0 = default no-flux, 1 = gradient               */
+    int32_t device;        /* CUDA device ordinal                             */
+    double  A_grad_south, A_grad_north;
+    /* y-slab decomposition: this context owns global rows
+       j in [slab_j0+1, slab_j0+slab_ny]; single GPU: 0, Ny.  The slab is
+       stored exactly like a (Nx, slab_ny) Field with Hy=3 halos.             */
+    int32_t slab_j0, slab_ny;
+    int32_t rank, world;   /* position of the slab in the y ring              */
+} swmhd_config;
+
+typedef struct swmhd_diag {
+    double ke, me, pe, total;   /* SWMHD_example.jl:74-77, divergence_sw_mhd.jl:71-74 */
+    double max_abs_u;           /* SWMHD_example.jl:57 (|uh/h| for DIVERGENCE, divergence_sw_mhd.jl:47,53) */
+    double max_abs_A, min_h;    /* same lines                                  */
+    double max_abs_div_hB;      /* max |dx(hBx)+dy(hBy)| at cell centres        */
+    double sum_h;               /* mass, sum over interior                      */
+    int32_t all_finite;         /* 0 if any of the four fields has NaN/Inf      */
+    int32_t reserved;
+} swmhd_diag;
+
+typedef struct swmhd_ctx swmhd_ctx;
+
+/* ShallowWaterModel(grid=..., ...) — SWMHD_example.jl:14-33, divergence_sw_mhd.jl:12-31 */
+int  swmhd_create(const swmhd_config *cfg, swmhd_ctx **out);
+void swmhd_destroy(swmhd_ctx *ctx);
+const char *swmhd_last_error(const swmhd_ctx *ctx); /* ctx may be NULL: last create error */
+int  swmhd_abi_version(void);
+
+/* set!(model, u=..., v=..., h=..., A=...) — SWMHD_example.jl:41, divergence_sw_mhd.jl:38.
+   host = parent array of the Field (this slab's rows), n = its length in doubles. */
+int  swmhd_set_field(swmhd_ctx *ctx, int field, const double *host, size_t n);
+/* interior(field)/parent(field) for callbacks and OutputWriters — SWMHD_example.jl:50-52,81-84 */
+int  swmhd_get_field(swmhd_ctx *ctx, int field, double *host, size_t n);
+size_t swmhd_field_len(const swmhd_ctx *ctx, int field);  /* doubles in the parent array */
+
+/* update_state!(model) = fill_halo_regions! on solution and tracers (after set!) */
+int  swmhd_fill_halos(swmhd_ctx *ctx);
+
+/* time_step!(model, dt) x nsteps with RungeKutta3 — SWMHD_example.jl:23,42,97.
+   Single-slab contexts only (world == 1). Blocking. */
+int  swmhd_step(swmhd_ctx *ctx, double dt, int nsteps);
+/* same, but diagnostics of the state at the START of each step are produced by
+   the stage-1 kernel at no extra HBM traffic and written to diags[0..nsteps) */
+int  swmhd_step_diag(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags);
+
+/* one RK3 substage (stage = 1,2,3), including the halo fill that follows it */
+int  swmhd_substage(swmhd_ctx *ctx, double dt, int stage);
+/* calculate_tendencies!(model): G^n of the current state into four host parent arrays */
+int  swmhd_tendencies(swmhd_ctx *ctx, double *const G_host[4], size_t n_each);
+
+/* the four energy means and the progress-callback reductions —
+   SWMHD_example.jl:47-63,67-77; divergence_sw_mhd.jl:42-59,63-75 */
+int  swmhd_diagnostics(swmhd_ctx *ctx, swmhd_diag *out);
+
+/* model.clock: time and iteration as advanced by the RK3 stages */
+double  swmhd_time(const swmhd_ctx *ctx);
+int64_t swmhd_iteration(const swmhd_ctx *ctx);
+int  swmhd_set_clock(swmhd_ctx *ctx, double time, int64_t iteration);
+
+/* ---- y-slab (multi-GPU) plumbing: one context per process per GPU ---------
+   The host owns the exchange (NCCL send/recv via torch.distributed, or MPI in
+   Julia).  Per substage:  swmhd_substage_edges -> exchange rows ->
+   swmhd_substage_interior -> swmhd_substage_finish.                          */
+int  swmhd_set_streams(swmhd_ctx *ctx, void *main_stream, void *edge_stream);
+int  swmhd_substage_edges(swmhd_ctx *ctx, double dt, int stage);    /* rows within 3 of a slab edge  */
+int  swmhd_substage_interior(swmhd_ctx *ctx, double dt, int stage); /* the rest, on the main stream   */
+int  swmhd_substage_finish(swmhd_ctx *ctx, int stage);              /* swap buffers, tick clock        */
+/* device pointer to the first of `nrows` contiguous parent rows of the NEW
+   state of `field`: which = 0 south send rows, 1 north send rows,
+   2 south halo (recv), 3 north halo (recv).  *row_doubles = Nx+6.           */
+int  swmhd_exchange_rows(swmhd_ctx *ctx, int field, int which,
+                         void **dev_ptr, int *nrows, size_t *row_doubles);
+int  swmhd_sync(swmhd_ctx *ctx);
+
+/* bookkeeping for bench.py: kernels launched since create, and device-side
+   duration of the last swmhd_step call measured with CUDA events (ms).     */
+int64_t swmhd_launch_count(const swmhd_ctx *ctx);
+double  swmhd_last_step_ms(const swmhd_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWMHD_ABI_H_ */
