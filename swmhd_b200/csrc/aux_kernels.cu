@@ -1,0 +1,168 @@
+// aux_kernels.cu — halo filling (fill_halo_regions!) and the diagnostic
+// reductions of the reference scripts (SWMHD_example.jl:47-63,67-77;
+// divergence_sw_mhd.jl:42-59,63-75).
+#include "kparams.h"
+#include <cmath>
+
+namespace swmhd {
+namespace {
+
+// One thread per halo cell.  Every halo cell reads its *interior* source directly
+// (x wrap and y wrap/mirror composed), so one launch fills edges and corners with
+// no ordering constraint between the x and y passes.
+__global__ void halo_kernel(const HaloParams p) {
+    const int k = blockIdx.y;
+    double *a = p.U[k];
+    const int Nx = p.Nx, Ny = p.Ny, P = p.P;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrow = p.j_hi - p.j_lo + 1;
+    const int nxw = nrow > 0 ? nrow * 6 : 0;
+    if (t < nxw) {                       // periodic x wrap of parent row r
+        int r = p.j_lo + t / 6, c = t % 6;
+        if (r >= p.rows[k]) return;
+        int dst = c < 3 ? c : Nx + c;    // 0,1,2 | Nx+3,Nx+4,Nx+5
+        int src = c < 3 ? Nx + c : c;    // Nx..Nx+2 | 3,4,5
+        a[(size_t)r * P + dst] = a[(size_t)r * P + src];
+        return;
+    }
+    t -= nxw;
+    if (t >= 6 * P) return;
+    const int slot = t / P, pi = t % P;
+    const int si = pi < 3 ? pi + Nx : (pi >= Nx + 3 ? pi - Nx : pi);   // x-wrapped source column
+    const bool south = slot < 3;
+    const int kk = south ? slot + 1 : slot - 2;                          // 1..3
+    if (p.y_mode == 0) return;
+    if (p.y_mode == 1) {
+        // Periodic: c[1-k] = c[Ny+1-k], c[Ny+k] = c[k]
+        int dj = south ? 1 - kk : Ny + kk, sj = south ? Ny + 1 - kk : kk;
+        a[(size_t)(dj + 2) * P + pi] = a[(size_t)(sj + 2) * P + si];
+        return;
+    }
+    if (south ? !p.first : !p.last) return;
+    if (k == 1) {                        // v|vh: impenetrable wall rows j = 1 and Ny+1
+        if (kk == 1) a[(size_t)((south ? 1 : Ny + 1) + 2) * P + pi] = 0.0;
+        return;
+    }
+    // centre-located in y: mirror (no-flux), with the gradient offset on A
+    int dj = south ? 1 - kk : Ny + kk, sj = south ? kk : Ny + 1 - kk;
+    double val = a[(size_t)(sj + 2) * P + si];
+    if (k == 3 && p.grad) {
+        if (south) val = val - p.gs * (double)(2 * kk - 1) * p.dy;
+        else       val = val + p.gn * (double)(2 * kk - 1) * p.dy;
+    }
+    a[(size_t)(dj + 2) * P + pi] = val;
+}
+
+// ---------------------------------------------------------------------------
+struct DiagAcc { double v[NDIAG]; };
+
+__device__ __forceinline__ double warp_sum(double x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double warp_max(double x) {
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, o));
+    return x;
+}
+__device__ __forceinline__ double warp_min(double x) {
+    for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_down_sync(0xffffffffu, x, o));
+    return x;
+}
+
+constexpr int DT = 256;
+
+__global__ void __launch_bounds__(DT) diag_kernel(const DiagParams p) {
+    const int Nx = p.Nx, Ny = p.Ny, P = p.P;
+    const double *u = p.U[0], *v = p.U[1], *h = p.U[2], *A = p.U[3];
+    auto ix = [&](int i, int j) { return (size_t)(i + 2) + (size_t)P * (size_t)(j + 2); };
+    auto sq = [](double x) { return x * x; };
+    auto ixf_h = [&](int i, int j) { return 0.5 * (h[ix(i - 1, j)] + h[ix(i, j)]); };
+    auto iyf_h = [&](int i, int j) { return 0.5 * (h[ix(i, j - 1)] + h[ix(i, j)]); };
+    auto dxA = [&](int i, int j) { return (A[ix(i, j)] - A[ix(i - 1, j)]) / p.dx; };
+    auto dyA = [&](int i, int j) { return (A[ix(i, j)] - A[ix(i, j - 1)]) / p.dy; };
+    // KE bracket u^2 + ℑxyᶠᶜᵃ(v^2) at fcc; ME bracket Bx^2 + ℑxyᶜᶠᵃ(By^2) at cfc
+    auto keb = [&](int i, int j) {
+        return sq(u[ix(i, j)]) + 0.5 * (0.5 * (sq(v[ix(i - 1, j)]) + sq(v[ix(i, j)])) +
+                                        0.5 * (sq(v[ix(i - 1, j + 1)]) + sq(v[ix(i, j + 1)])));
+    };
+    auto sqBx = [&](int i, int j) { return sq(-dyA(i, j) / iyf_h(i, j)); };
+    auto sqBy = [&](int i, int j) { return sq(dxA(i, j) / ixf_h(i, j)); };
+    auto meb = [&](int i, int j) {
+        return sqBx(i, j) + 0.5 * (0.5 * (sqBy(i, j - 1) + sqBy(i + 1, j - 1)) + 0.5 * (sqBy(i, j) + sqBy(i + 1, j)));
+    };
+    auto hBx = [&](int i, int j) { return -(0.5 * (0.5 * (dyA(i - 1, j) + dyA(i, j)) + 0.5 * (dyA(i - 1, j + 1) + dyA(i, j + 1)))); };
+    auto hBy = [&](int i, int j) { return 0.5 * (0.5 * (dxA(i, j - 1) + dxA(i + 1, j - 1)) + 0.5 * (dxA(i, j) + dxA(i + 1, j))); };
+
+    double ke = 0, me = 0, pe = 0, sh = 0, mu = 0, mA = 0, mh = INFINITY, md = 0, nf = 0;
+    const long long ncell = (long long)Nx * Ny;
+    for (long long c = (long long)blockIdx.x * DT + threadIdx.x; c < ncell; c += (long long)gridDim.x * DT) {
+        int i = (int)(c % Nx) + 1, j = (int)(c / Nx) + 1;
+        double hh = h[ix(i, j)], aa = A[ix(i, j)], uu = u[ix(i, j)], vv = v[ix(i, j)];
+        double wgt = (p.form == 0) ? 0.5 * hh : 0.5 * (1.0 / hh);
+        ke += wgt * (0.5 * (keb(i, j) + keb(i + 1, j)));
+        me += (0.5 * hh) * (0.5 * (meb(i, j) + meb(i, j + 1)));
+        double dh = hh - p.h_ref;
+        pe += (0.5 * p.g) * (dh * dh);
+        sh += hh;
+        double speed = (p.form == 0) ? fabs(uu) : fabs(uu / ixf_h(i, j));
+        mu = fmax(mu, speed);
+        mA = fmax(mA, fabs(aa));
+        mh = fmin(mh, hh);
+        md = fmax(md, fabs((hBx(i + 1, j) - hBx(i, j)) / p.dx + (hBy(i, j + 1) - hBy(i, j)) / p.dy));
+        if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) nf += 1.0;
+    }
+    __shared__ double red[NDIAG][DT / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double r[NDIAG] = {warp_sum(ke), warp_sum(me), warp_sum(pe), warp_sum(sh), warp_max(mu),
+                       warp_max(mA), warp_min(mh), warp_max(md), warp_sum(nf)};
+    if (lane == 0)
+        for (int q = 0; q < NDIAG; q++) red[q][wid] = r[q];
+    __syncthreads();
+    if (threadIdx.x < NDIAG) {
+        int q = threadIdx.x;
+        double acc = red[q][0];
+        for (int w = 1; w < DT / 32; w++) {
+            if (q == 6) acc = fmin(acc, red[q][w]);
+            else if (q == 4 || q == 5 || q == 7) acc = fmax(acc, red[q][w]);
+            else acc += red[q][w];
+        }
+        p.partials[(size_t)blockIdx.x * NDIAG + q] = acc;
+    }
+}
+
+// fixed-order final reduction: deterministic sums
+__global__ void diag_final_kernel(const double *partials, int nblocks, double *out) {
+    int q = threadIdx.x;
+    if (q >= NDIAG) return;
+    double acc = partials[q];
+    for (int b = 1; b < nblocks; b++) {
+        double x = partials[(size_t)b * NDIAG + q];
+        if (q == 6) acc = fmin(acc, x);
+        else if (q == 4 || q == 5 || q == 7) acc = fmax(acc, x);
+        else acc += x;
+    }
+    out[q] = acc;
+}
+
+} // namespace
+
+cudaError_t launch_halo(const HaloParams &p, cudaStream_t st) {
+    int nrow = p.j_hi - p.j_lo + 1;
+    int n = (nrow > 0 ? nrow * 6 : 0) + 6 * p.P;
+    dim3 grid((n + 255) / 256, 4);
+    halo_kernel<<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+int diag_blocks(int Nx, int Ny) {
+    long long n = ((long long)Nx * Ny + DT - 1) / DT;
+    return (int)(n < 148 * 8 ? n : 148 * 8);
+}
+
+cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st) {
+    diag_kernel<<<p.nblocks, DT, 0, st>>>(p);
+    diag_final_kernel<<<1, 32, 0, st>>>(p.partials, p.nblocks, out9);
+    return cudaGetLastError();
+}
+
+} // namespace swmhd

@@ -1,0 +1,57 @@
+// Internal launch-parameter block shared by the CUDA translation units.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cuda_runtime.h>
+
+namespace swmhd {
+
+// RK3 constants of Oceananigans' RungeKutta3TimeStepper
+constexpr double RK_GAMMA[3] = {8.0 / 15.0, 5.0 / 12.0, 3.0 / 4.0};
+constexpr double RK_ZETA[3]  = {0.0, -17.0 / 60.0, -5.0 / 12.0};
+
+struct KParams {
+    int Nx, Ny;          // local interior size (Ny = rows of this y-slab)
+    int P;               // row pitch of every parent array = Nx + 6
+    int gj0, NyG;        // global row of local row j is gj0 + j; global Ny
+    int by;              // topo_y == Bounded
+    int tile_row0, tile_rows; // first tile-row and number of tile-rows of this launch
+    int rows[4];         // parent rows per field (Ny+6, v: +1 when Bounded-y)
+    double dx, dy, rdx, rdy, inv_az, g, f, eps;
+    double dt, gam, zet, dtgam;  // stage coefficients; dtgam = dt*gam (stage 1)
+    const double *Uo[4]; // state at the start of the substage (halos valid)
+    double *Un[4];       // state after the substage (interior written)
+    double *G[4];        // G^- on entry (stages 2,3), G^n on exit (stages 1,2)
+    double *diag;        // per-CTA diagnostic partials (stage-1 fusion), or nullptr
+};
+
+struct HaloParams {
+    int Nx, Ny, P;
+    int by, first, last;   // Bounded-y; this slab touches the south / north wall
+    int y_mode;            // 0: no y fill, 1: periodic wrap owned by this context, 2: wall BCs
+    int grad;              // gradient BC on A
+    double gs, gn, dy;     // A_grad_south, A_grad_north, dy
+    int j_lo, j_hi;        // x-wrap parent rows (inclusive; empty if j_hi < j_lo)
+    double *U[4];
+    int rows[4];
+};
+
+struct DiagParams {
+    int Nx, Ny, P, form;
+    double dx, dy, g, h_ref;
+    const double *U[4];
+    double *partials;      // [nblocks][NDIAG]
+    int nblocks;
+};
+
+constexpr int NDIAG = 9; // ke, me, pe, sum_h, max|u|, max|A|, min h, max|div hB|, nonfinite count
+
+// kernel launchers (one strict + one fast instantiation of substage_kernel.cu)
+cudaError_t launch_substage_strict(const KParams &p, int form, int stage, cudaStream_t st);
+cudaError_t launch_substage_fast(const KParams &p, int form, int stage, cudaStream_t st);
+void substage_tile(int *tx, int *ty);
+cudaError_t launch_halo(const HaloParams &p, cudaStream_t st);
+cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st);
+int diag_blocks(int Nx, int Ny);
+
+} // namespace swmhd
