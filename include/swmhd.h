@@ -165,6 +165,9 @@ int  swmhd_sync(swmhd_ctx *ctx);
 
 /* bookkeeping for bench.py: kernels launched since create, and device-side
    duration of the last swmhd_step call measured with CUDA events (ms).     */
+/* nsteps RK3 steps with a CUDA-event pair around every fused substage-kernel launch;
+   out_ms[s] = mean device time of the stage-(s+1) kernel (roofline measurement). */
+int  swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]);
 int64_t swmhd_launch_count(const swmhd_ctx *ctx);
 double  swmhd_last_step_ms(const swmhd_ctx *ctx);
 

@@ -87,6 +87,12 @@ class Context:
         self._ck(self.lib.swmhd_step_diag(self._h, float(dt), int(nsteps), arr))
         return [d.as_dict() for d in arr]
 
+    def step_profile(self, dt, nsteps=1):
+        """Mean device time (ms) of the three fused substage kernels over nsteps steps."""
+        out = (C.c_double * 3)()
+        self._ck(self.lib.swmhd_step_profile(self._h, float(dt), int(nsteps), out))
+        return list(out)
+
     def substage(self, dt, stage):
         self._ck(self.lib.swmhd_substage(self._h, float(dt), int(stage)))
 

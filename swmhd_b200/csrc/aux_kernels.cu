@@ -64,10 +64,6 @@ __device__ __forceinline__ double warp_max(double x) {
     for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, o));
     return x;
 }
-__device__ __forceinline__ double warp_min(double x) {
-    for (int o = 16; o > 0; o >>= 1) x = fmin(x, __shfl_down_sync(0xffffffffu, x, o));
-    return x;
-}
 
 constexpr int DT = 256;
 
@@ -93,7 +89,7 @@ __global__ void __launch_bounds__(DT) diag_kernel(const DiagParams p) {
     auto hBx = [&](int i, int j) { return -(0.5 * (0.5 * (dyA(i - 1, j) + dyA(i, j)) + 0.5 * (dyA(i - 1, j + 1) + dyA(i, j + 1)))); };
     auto hBy = [&](int i, int j) { return 0.5 * (0.5 * (dxA(i, j - 1) + dxA(i + 1, j - 1)) + 0.5 * (dxA(i, j) + dxA(i + 1, j))); };
 
-    double ke = 0, me = 0, pe = 0, sh = 0, mu = 0, mA = 0, mh = INFINITY, md = 0, nf = 0;
+    double ke = 0, me = 0, pe = 0, sh = 0, mu = 0, mA = 0, mh = -INFINITY, md = 0, nf = 0;
     const long long ncell = (long long)Nx * Ny;
     for (long long c = (long long)blockIdx.x * DT + threadIdx.x; c < ncell; c += (long long)gridDim.x * DT) {
         int i = (int)(c % Nx) + 1, j = (int)(c / Nx) + 1;
@@ -107,14 +103,14 @@ __global__ void __launch_bounds__(DT) diag_kernel(const DiagParams p) {
         double speed = (p.form == 0) ? fabs(uu) : fabs(uu / ixf_h(i, j));
         mu = fmax(mu, speed);
         mA = fmax(mA, fabs(aa));
-        mh = fmin(mh, hh);
+        mh = fmax(mh, -hh);
         md = fmax(md, fabs((hBx(i + 1, j) - hBx(i, j)) / p.dx + (hBy(i, j + 1) - hBy(i, j)) / p.dy));
         if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) nf += 1.0;
     }
     __shared__ double red[NDIAG][DT / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double r[NDIAG] = {warp_sum(ke), warp_sum(me), warp_sum(pe), warp_sum(sh), warp_max(mu),
-                       warp_max(mA), warp_min(mh), warp_max(md), warp_sum(nf)};
+                       warp_max(mA), warp_max(mh), warp_max(md), warp_sum(nf)};
     if (lane == 0)
         for (int q = 0; q < NDIAG; q++) red[q][wid] = r[q];
     __syncthreads();
@@ -122,26 +118,37 @@ __global__ void __launch_bounds__(DT) diag_kernel(const DiagParams p) {
         int q = threadIdx.x;
         double acc = red[q][0];
         for (int w = 1; w < DT / 32; w++) {
-            if (q == 6) acc = fmin(acc, red[q][w]);
-            else if (q == 4 || q == 5 || q == 7) acc = fmax(acc, red[q][w]);
+            if (q >= 4 && q <= 7) acc = fmax(acc, red[q][w]);
             else acc += red[q][w];
         }
         p.partials[(size_t)blockIdx.x * NDIAG + q] = acc;
     }
 }
 
-// fixed-order final reduction: deterministic sums
-__global__ void diag_final_kernel(const double *partials, int nblocks, double *out) {
-    int q = threadIdx.x;
-    if (q >= NDIAG) return;
-    double acc = partials[q];
-    for (int b = 1; b < nblocks; b++) {
-        double x = partials[(size_t)b * NDIAG + q];
-        if (q == 6) acc = fmin(acc, x);
-        else if (q == 4 || q == 5 || q == 7) acc = fmax(acc, x);
-        else acc += x;
+// fixed-order final reduction (deterministic): thread t folds partials t, t+FT, ... in order,
+// then a fixed binary tree over the FT lanes.  Slots 4..7 are maxima, the rest sums.
+constexpr int FT = 1024;
+__global__ void __launch_bounds__(FT) diag_final_kernel(const double *partials, int nblocks, double *out) {
+    __shared__ double sh[FT];
+    for (int q = 0; q < NDIAG; q++) {
+        const bool is_max = (q >= 4 && q <= 7);
+        double acc = is_max ? -INFINITY : 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += FT) {
+            double x = partials[(size_t)b * NDIAG + q];
+            acc = is_max ? fmax(acc, x) : acc + x;
+        }
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (int s = FT / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                double x = sh[threadIdx.x + s];
+                sh[threadIdx.x] = is_max ? fmax(sh[threadIdx.x], x) : sh[threadIdx.x] + x;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[q] = sh[0];
+        __syncthreads();
     }
-    out[q] = acc;
 }
 
 } // namespace
@@ -161,7 +168,12 @@ int diag_blocks(int Nx, int Ny) {
 
 cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st) {
     diag_kernel<<<p.nblocks, DT, 0, st>>>(p);
-    diag_final_kernel<<<1, 32, 0, st>>>(p.partials, p.nblocks, out9);
+    diag_final_kernel<<<1, FT, 0, st>>>(p.partials, p.nblocks, out9);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_diag_final(const double *partials, int nblocks, double *out9, cudaStream_t st) {
+    diag_final_kernel<<<1, FT, 0, st>>>(partials, nblocks, out9);
     return cudaGetLastError();
 }
 

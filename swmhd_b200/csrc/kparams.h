@@ -19,10 +19,11 @@ struct KParams {
     int rows[4];         // parent rows per field (Ny+6, v: +1 when Bounded-y)
     double dx, dy, rdx, rdy, inv_az, g, f, eps;
     double dt, gam, zet, dtgam;  // stage coefficients; dtgam = dt*gam (stage 1)
+    double h_ref;                // h_i of the potential-energy diagnostic
     const double *Uo[4]; // state at the start of the substage (halos valid)
     double *Un[4];       // state after the substage (interior written)
     double *G[4];        // G^- on entry (stages 2,3), G^n on exit (stages 1,2)
-    double *diag;        // per-CTA diagnostic partials (stage-1 fusion), or nullptr
+    double *diag;        // per-CTA diagnostic partials [tiles][NDIAG] (stage-1 DIAG variant), or nullptr
 };
 
 struct HaloParams {
@@ -44,7 +45,7 @@ struct DiagParams {
     int nblocks;
 };
 
-constexpr int NDIAG = 9; // ke, me, pe, sum_h, max|u|, max|A|, min h, max|div hB|, nonfinite count
+constexpr int NDIAG = 9; // sums: ke, me, pe, sum_h [0..3]; maxima: |u|, |A|, -h, |div hB| [4..7]; nonfinite count [8]
 
 // kernel launchers (one strict + one fast instantiation of substage_kernel.cu)
 cudaError_t launch_substage_strict(const KParams &p, int form, int stage, cudaStream_t st);
@@ -52,6 +53,7 @@ cudaError_t launch_substage_fast(const KParams &p, int form, int stage, cudaStre
 void substage_tile(int *tx, int *ty);
 cudaError_t launch_halo(const HaloParams &p, cudaStream_t st);
 cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st);
+cudaError_t launch_diag_final(const double *partials, int nblocks, double *out9, cudaStream_t st);
 int diag_blocks(int Nx, int Ny);
 
 } // namespace swmhd

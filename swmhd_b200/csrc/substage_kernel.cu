@@ -5,19 +5,23 @@
 // Lorentz-force closures inlined:
 //   FORM 0  VectorInvariantFormulation + jacobian_formulation/sw_mhd_jacobian_functions.jl:1-26
 //   FORM 1  ConservativeFormulation    + divergence_formulation/sw_mhd_divergence_functions.jl:1-170
+// and, in the stage-1 DIAG variant, the energy / max / min / div(hB) diagnostics of
+// SWMHD_example.jl:47-77 evaluated on the tile that is already staged (0 extra HBM bytes).
 //
 // This file is compiled twice:
 //   -DSWMHD_STRICT=1 -fmad=false : operation order, IEEE divisions and rounding of the
 //                                  specification -> bit-identical to oracle/swmhd_oracle.c
-//   -DSWMHD_STRICT=0             : FMA contraction, one-division WENO weights, Newton reciprocals
+//   -DSWMHD_STRICT=0             : explicit FMAs, one-division WENO-Z weights, telescoped
+//                                  difference-of-average operators, Newton reciprocals
 //
-// Tile scheme: a CTA owns TX x TY cells.  P0 stages u,v,h,A with a 3-cell halo in
-// shared memory; P1 builds the derived staggered fields every stencil shares
-// (zeta, velocity-stencil averages, K, Bx, By | hBx, hBy, Bx, By, h at corners);
-// P2 evaluates every face flux exactly once (upwind side selected by sign, which is
-// bit-identical to upwind_biased_product for finite data); P3 differences the
-// fluxes, adds the remaining terms, applies U += dt(gamma G^n + zeta G^-) and
-// writes U_new and G^n.  HBM traffic per cell: 4-8 reads + 4-8 writes of doubles.
+// Tile scheme: a CTA owns TX x TY cells.
+//   P0  stage u,v,h,A with a 3-cell halo in shared memory
+//   P1  one balanced task list: derived staggered fields (zeta, velocity-stencil
+//       averages, K, Bx, By | hBx, hBy, Bx, By, face h) and every face flux exactly once
+//       (upwind side selected by sign: bit-identical to upwind_biased_product for finite data)
+//   P2  per cell: difference the fluxes, vorticity advection, pressure, Coriolis,
+//       Lorentz force, U += dt(gamma G^n + zeta G^-), store U_new and G^n.
+// HBM traffic per cell and substage: 4-8 reads + 4-8 writes of doubles (algorithmic).
 #include "kparams.h"
 
 #ifndef SWMHD_STRICT
@@ -34,7 +38,14 @@ namespace {
 #endif
 
 constexpr int TX = 32, TY = 8, NT = 256;
-constexpr int W = TX + 6, HT = TY + 6, SZ = W * HT;
+constexpr int W = TX + 6, HT = TY + 6, SZ = W * HT;        // raw tiles: [HT][W]
+
+// compact derived / flux arrays: (pitch, rows)
+constexpr int ZP = TX + 5, ZR = TY + 5;     // ffc points a in [1,TX+5], b in [1,TY+5]
+constexpr int CP = TX + 2, CR = TY + 2;     // ccc points a in [2,TX+3], b in [2,TY+3]
+constexpr int XP = TX + 1, XR = TY;         // x-face-like a in [a0,a0+TX], b in [3,TY+2]
+constexpr int YP = TX,     YR = TY + 1;     // y-face-like a in [3,TX+2],  b in [b0,b0+TY]
+constexpr int BP = TX + 4, BR = TY + 4;     // divergence-form B fields a in [1,TX+4], b in [1,TY+4]
 
 // ---------------------------------------------------------------------------
 // arithmetic primitives
@@ -59,7 +70,8 @@ __device__ __forceinline__ double fdiv(double a, double b) { return a * frcp(b);
 #define DIVAZ(x) ((x) * p.inv_az)
 #endif
 
-// WENO5 smoothness indicators; a..e = psi[f-3..f+1] in left orientation
+// ---- WENO5-Z.  a..e = psi[f-3..f+1] in upwind ("left") orientation ------------
+#if SWMHD_STRICT
 __device__ __forceinline__ void weno_beta(double a, double b, double c, double d, double e,
                                           double &b0, double &b1, double &b2) {
     double D0 = c - 2.0 * d + e, E0 = 3.0 * c - 4.0 * d + e;
@@ -69,11 +81,8 @@ __device__ __forceinline__ void weno_beta(double a, double b, double c, double d
     b1 = (13.0 / 12.0) * (D1 * D1) + 0.25 * (E1 * E1);
     b2 = (13.0 / 12.0) * (D2 * D2) + 0.25 * (E2 * E2);
 }
-
-// Z-weighted blend of the three candidate values
 __device__ __forceinline__ double weno_blend(double a, double b, double c, double d, double e,
                                              double b0, double b1, double b2, double eps) {
-#if SWMHD_STRICT
     double p0 = (2.0 * c + 5.0 * d - e) / 6.0;
     double p1 = (-b + 5.0 * c + 2.0 * d) / 6.0;
     double p2 = (2.0 * a - 7.0 * b + 11.0 * c) / 6.0;
@@ -85,35 +94,65 @@ __device__ __forceinline__ double weno_blend(double a, double b, double c, doubl
     double sum = a0 + a1 + a2;
     double w0 = a0 / sum, w1 = a1 / sum, w2 = a2 / sum;
     return w0 * p0 + w1 * p1 + w2 * p2;
-#else
-    // alpha_k = C_k (1 + tau^2/c_k^2), c_k = beta_k + eps.  Multiply numerator and
-    // denominator of sum(alpha p)/sum(alpha) by prod(c_k^2): one division in total.
-    double P0 = 2.0 * c + 5.0 * d - e;
-    double P1 = -b + 5.0 * c + 2.0 * d;
-    double P2 = 2.0 * a - 7.0 * b + 11.0 * c;
-    double c0 = b0 + eps, c1 = b1 + eps, c2 = b2 + eps;
-    double tau = b2 - b0, t2 = tau * tau;
-    double s0 = c0 * c0, s1 = c1 * c1, s2 = c2 * c2;
-    double a0 = (0.3 * (s0 + t2)) * (s1 * s2);
-    double a1 = (0.6 * (s1 + t2)) * (s0 * s2);
-    double a2 = (0.1 * (s2 + t2)) * (s0 * s1);
-    double num = a0 * P0 + a1 * P1 + a2 * P2;
-    double den = 6.0 * (a0 + a1 + a2);
-    return num * frcp(den);
-#endif
 }
-
 __device__ __forceinline__ double weno5(double a, double b, double c, double d, double e, double eps) {
     double b0, b1, b2;
     weno_beta(a, b, c, d, e, b0, b1, b2);
     return weno_blend(a, b, c, d, e, b0, b1, b2, eps);
 }
+// zeta with VelocityStencil smoothness: beta_k = (beta_k[ℑy u] + beta_k[ℑx v]) / 2
+__device__ __forceinline__ double weno5_vs(const double *qz, const double *qu, const double *qv, int s, double eps) {
+    double bu0, bu1, bu2, bv0, bv1, bv2;
+    weno_beta(qu[0], qu[s], qu[2 * s], qu[3 * s], qu[4 * s], bu0, bu1, bu2);
+    weno_beta(qv[0], qv[s], qv[2 * s], qv[3 * s], qv[4 * s], bv0, bv1, bv2);
+    return weno_blend(qz[0], qz[s], qz[2 * s], qz[3 * s], qz[4 * s],
+                      0.5 * (bu0 + bv0), 0.5 * (bu1 + bv1), 0.5 * (bu2 + bv2), eps);
+}
+#else
+// acc + k13*D^2 + k14*E^2 for the three candidate stencils (k13 = 13/12*s, k14 = 1/4*s)
+__device__ __forceinline__ void weno_beta_acc(double a, double b, double c, double d, double e, double k13, double k14,
+                                              double &c0, double &c1, double &c2) {
+    double D0 = fma(-2.0, d, c + e), E0 = fma(3.0, c, fma(-4.0, d, e));
+    double D1 = fma(-2.0, c, b + d), E1 = b - d;
+    double D2 = fma(-2.0, b, a + c), E2 = fma(3.0, c, fma(-4.0, b, a));
+    c0 = fma(k13 * D0, D0, fma(k14 * E0, E0, c0));
+    c1 = fma(k13 * D1, D1, fma(k14 * E1, E1, c1));
+    c2 = fma(k13 * D2, D2, fma(k14 * E2, E2, c2));
+}
+// alpha_k = C_k (1 + tau^2/c_k^2), c_k = beta_k + eps.  Multiplying numerator and denominator of
+// sum(alpha_k p_k)/sum(alpha_k) by prod(c_k^2) leaves one division:  alpha_k ~ C_k (S + tau^2 q_k),
+// S = s0 s1 s2, q_k = S/s_k, s_k = c_k^2;  C_k/6 is folded into the candidate polynomials.
+__device__ __forceinline__ double weno_blend_c(double a, double b, double c, double d, double e,
+                                               double c0, double c1, double c2) {
+    double tau = c2 - c0, t2 = tau * tau;
+    double s0 = c0 * c0, s1 = c1 * c1, s2 = c2 * c2;
+    double q2 = s0 * s1, q0 = s1 * s2, q1 = s0 * s2, S = q2 * s2;
+    double a0 = fma(t2, q0, S), a1 = fma(t2, q1, S), a2 = fma(t2, q2, S);
+    double P0 = fma(0.1, c, fma(0.25, d, -0.05 * e));                       // 0.3/6 (2c + 5d - e)
+    double P1 = fma(-0.1, b, fma(0.5, c, 0.2 * d));                         // 0.6/6 (-b + 5c + 2d)
+    double P2 = fma(1.0 / 30.0, a, fma(-7.0 / 60.0, b, (11.0 / 60.0) * c)); // 0.1/6 (2a - 7b + 11c)
+    double num = fma(a0, P0, fma(a1, P1, a2 * P2));
+    double den = fma(0.3, a0, fma(0.6, a1, 0.1 * a2));
+    return num * frcp(den);
+}
+__device__ __forceinline__ double weno5(double a, double b, double c, double d, double e, double eps) {
+    double c0 = eps, c1 = eps, c2 = eps;
+    weno_beta_acc(a, b, c, d, e, 13.0 / 12.0, 0.25, c0, c1, c2);
+    return weno_blend_c(a, b, c, d, e, c0, c1, c2);
+}
+__device__ __forceinline__ double weno5_vs(const double *qz, const double *qu, const double *qv, int s, double eps) {
+    double c0 = eps, c1 = eps, c2 = eps;
+    weno_beta_acc(qu[0], qu[s], qu[2 * s], qu[3 * s], qu[4 * s], 13.0 / 24.0, 0.125, c0, c1, c2);
+    weno_beta_acc(qv[0], qv[s], qv[2 * s], qv[3 * s], qv[4 * s], 13.0 / 24.0, 0.125, c0, c1, c2);
+    return weno_blend_c(qz[0], qz[s], qz[2 * s], qz[3 * s], qz[4 * s], c0, c1, c2);
+}
+#endif
 
 __device__ __forceinline__ double sym4(double a, double b, double c, double d) {
 #if SWMHD_STRICT
     return (7.0 * (b + c) - (a + d)) / 12.0;
 #else
-    return (7.0 * (b + c) - (a + d)) * (1.0 / 12.0);
+    return fma(7.0 / 12.0, b + c, (-1.0 / 12.0) * (a + d));
 #endif
 }
 __device__ __forceinline__ double sym2(double b, double c) { return 0.5 * (b + c); }
@@ -123,66 +162,84 @@ __device__ __forceinline__ double third(double x2, double x5, double xm) { // (2
 #if SWMHD_STRICT
     return (2.0 * x2 + 5.0 * x5 - xm) / 6.0;
 #else
-    return (2.0 * x2 + 5.0 * x5 - xm) * (1.0 / 6.0);
+    return fma(1.0 / 3.0, x2, fma(5.0 / 6.0, x5, (-1.0 / 6.0) * xm));
 #endif
 }
 __device__ __forceinline__ double thirdR(double xm, double x5, double x2) { // (-xm + 5*x5 + 2*x2)/6
 #if SWMHD_STRICT
     return (-xm + 5.0 * x5 + 2.0 * x2) / 6.0;
 #else
-    return (-xm + 5.0 * x5 + 2.0 * x2) * (1.0 / 6.0);
+    return fma(-1.0 / 6.0, xm, fma(5.0 / 6.0, x5, (1.0 / 3.0) * x2));
+#endif
+}
+
+// ℑxy of four corner values, 0.5*(0.5*(a+b) + 0.5*(c+d))
+__device__ __forceinline__ double avg4(double a, double b, double c, double d) {
+#if SWMHD_STRICT
+    return 0.5 * (0.5 * (a + b) + 0.5 * (c + d));
+#else
+    return 0.25 * ((a + b) + (c + d));
 #endif
 }
 
 // Bounded-y wall buffer (oracle ybuf): footprint f-n..f+n-1 must stay in [1,hi]
 __device__ __forceinline__ bool ybuf(int by, int f, int n, int hi) { return by && (f - n < 1 || f + n - 1 > hi); }
 
-#define AT(arr, a, b) arr[(b) * W + (a)]
-
-// The five samples of the upwind-biased WENO5 stencil of face f along a line with
-// element stride `st`: left-biased (vel > 0) psi[f-3..f+1], right-biased the mirror
-// psi[f+2..f-2].  Selecting the side by the sign of the advecting velocity is
-// bit-identical to upwind_biased_product (the other side is multiplied by exactly 0).
-#define Q5(q, s) (q)[0], (q)[(s)], (q)[2 * (s)], (q)[3 * (s)], (q)[4 * (s)]
-
-__device__ __forceinline__ double upwind_weno_x(const double *arr, int lf, int lj, double vel, double eps) {
+// The five samples of the upwind-biased WENO5 stencil of face f along a line with element
+// stride st: left-biased (vel > 0) psi[f-3..f+1], right-biased the mirror psi[f+2..f-2].
+// ctr points at psi[f]; returns vel * psi_upwind (== upwind_biased_product, other side * 0).
+__device__ __forceinline__ double upwind_weno(const double *ctr, int st, double vel, double eps) {
     const bool pos = vel > 0.0;
-    const double *q = &AT(arr, pos ? lf - 3 : lf + 2, lj);
-    const int s = pos ? 1 : -1;
-    return vel * weno5(Q5(q, s), eps);
+    const double *q = pos ? ctr - 3 * st : ctr + 2 * st;
+    const int s = pos ? st : -st;
+    return vel * weno5(q[0], q[s], q[2 * s], q[3 * s], q[4 * s], eps);
 }
-__device__ __forceinline__ double upwind_weno_y(const double *arr, int li, int lf, double vel, double eps, bool buf) {
-    if (buf) return vel * sym2(AT(arr, li, lf - 1), AT(arr, li, lf));
-    const bool pos = vel > 0.0;
-    const double *q = &AT(arr, li, pos ? lf - 3 : lf + 2);
-    const int s = pos ? W : -W;
-    return vel * weno5(Q5(q, s), eps);
+__device__ __forceinline__ double upwind_weno_buf(const double *ctr, int st, double vel, double eps, bool buf) {
+    if (buf) return vel * sym2(ctr[-st], ctr[0]);
+    return upwind_weno(ctr, st, vel, eps);
 }
-// zeta with VelocityStencil smoothness: beta_k = (beta_k[ℑy u] + beta_k[ℑx v]) / 2 (SURVEY A.3)
-__device__ __forceinline__ double upwind_weno_vs(const double *z, const double *ut, const double *vt,
-                                                 int off, int s, double eps) {
-    double bu0, bu1, bu2, bv0, bv1, bv2;
-    const double *qu = ut + off, *qv = vt + off, *qz = z + off;
-    weno_beta(Q5(qu, s), bu0, bu1, bu2);
-    weno_beta(Q5(qv, s), bv0, bv1, bv2);
-    return weno_blend(Q5(qz, s), 0.5 * (bu0 + bv0), 0.5 * (bu1 + bv1), 0.5 * (bu2 + bv2), eps);
-}
-
-// sw_mhd_divergence_functions.jl:3 with the sign selected (exact for finite L, R)
 __device__ __forceinline__ double upwind_sel(double vel, double L, double R) {
-    if (vel > 0.0) return vel * L;
-    if (vel < 0.0) return vel * R;
-    return 0.0;
+    return vel * (vel > 0.0 ? L : R);
+}
+
+#define RAW(arr, a, b) arr[(b) * W + (a)]
+
+__device__ __forceinline__ double warp_sum(double x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double warp_max(double x) {
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, o));
+    return x;
 }
 
 // ---------------------------------------------------------------------------
-template <int FORM> struct Smem;
-template <> struct Smem<0> { static constexpr int NARR = 14; };
-template <> struct Smem<1> { static constexpr int NARR = 23; };
+constexpr int NDG_ = YP * YR + XP * (TY + 2);   // diag scratch: sqBx (YP*YR) + sqBy (XP*(TY+2))
+template <int FORM, bool DIAG> struct SmemLayout;
+template <bool DIAG> struct SmemLayout<0, DIAG> {
+    static constexpr int o_z = 4 * SZ, o_ut = o_z + ZP * ZR, o_vt = o_ut + ZP * ZR;
+    static constexpr int o_K = o_vt + ZP * ZR, o_Bx = o_K + CP * CR, o_By = o_Bx + CP * CR;
+    static constexpr int o_Fxh = o_By + CP * CR, o_FxA = o_Fxh + XP * XR;
+    static constexpr int o_Fyh = o_FxA + XP * XR, o_FyA = o_Fyh + YP * YR;
+    static constexpr int o_dg = o_FyA + YP * YR;
+    static constexpr int total = o_dg + (DIAG ? NDG_ : 0);
+};
+template <bool DIAG> struct SmemLayout<1, DIAG> {
+    static constexpr int o_hBx = 4 * SZ, o_hBy = o_hBx + BP * BR, o_Bx = o_hBy + BP * BR, o_By = o_Bx + BP * BR;
+    static constexpr int o_hx = o_By + BP * BR, o_hy = o_hx + BP * BR, o_hff = o_hy + BP * BR;
+    static constexpr int o_Fuu = o_hff + XP * YR, o_Lxx = o_Fuu + XP * XR, o_Fuv = o_Lxx + XP * XR, o_Lxy = o_Fuv + XP * XR;
+    static constexpr int o_Tx = o_Lxy + XP * XR, o_uq = o_Tx + XP * XR;
+    static constexpr int o_Fvu = o_uq + XP * XR, o_Lyx = o_Fvu + YP * YR, o_Fvv = o_Lyx + YP * YR, o_Lyy = o_Fvv + YP * YR;
+    static constexpr int o_Ty = o_Lyy + YP * YR, o_vq = o_Ty + YP * YR;
+    static constexpr int o_dg = o_vq + YP * YR;
+    static constexpr int total = o_dg + (DIAG ? NDG_ : 0);
+};
 
-template <int FORM, int STAGE>  // STAGE 1,2,3; 0 = tendencies only (G written, U untouched)
-__global__ void __launch_bounds__(NT, 2) substage_kernel(const KParams p) {
+// STAGE 1,2,3; 0 = tendencies only (G written, U untouched).  DIAG only with STAGE 1.
+template <int FORM, int STAGE, bool DIAG>
+__global__ void __launch_bounds__(NT, 3) substage_kernel(const KParams p) {
     extern __shared__ double smem[];
+    using L = SmemLayout<FORM, DIAG>;
     double *s_u = smem, *s_v = smem + SZ, *s_h = smem + 2 * SZ, *s_A = smem + 3 * SZ;
     const int tid = threadIdx.x;
     const int i0 = blockIdx.x * TX + 1;                     // logical (1-based) first cell
@@ -190,10 +247,24 @@ __global__ void __launch_bounds__(NT, 2) substage_kernel(const KParams p) {
     const int Nx = p.Nx, Ny = p.Ny, P = p.P;
     const double eps = p.eps;
 
+    // own cell of this thread
+    const int tx = tid % TX, ty = tid / TX;
+    const int li = tx + 3, lj = ty + 3;
+    const int i = i0 + tx, j = j0 + ty;
+    const bool active = (i <= Nx) && (j <= Ny);
+    const int gj = p.gj0 + j;                               // global row (wall logic)
+    const size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(j + 2);
+
+    // G^- of the own cell: issue the loads now, consume them after the tendencies
+    double Gm0 = 0.0, Gm1 = 0.0, Gm2 = 0.0, Gm3 = 0.0;
+    if constexpr (STAGE >= 2) {
+        if (active) { Gm0 = p.G[0][gcell]; Gm1 = p.G[1][gcell]; Gm2 = p.G[2][gcell]; Gm3 = p.G[3][gcell]; }
+    }
+
     // ---- P0: stage the four fields with a 3-cell halo -------------------------------
     for (int t = tid; t < SZ; t += NT) {
-        int li = t % W, lj = t / W;
-        int pi = i0 - 1 + li, pj = j0 - 1 + lj;             // parent (0-based) column / row
+        int a = t % W, b = t / W;
+        int pi = i0 - 1 + a, pj = j0 - 1 + b;               // parent (0-based) column / row
         bool okx = pi < P;
         size_t g = (size_t)pi + (size_t)P * (size_t)pj;
         s_u[t] = (okx && pj < p.rows[0]) ? p.Uo[0][g] : 0.0;
@@ -203,292 +274,417 @@ __global__ void __launch_bounds__(NT, 2) substage_kernel(const KParams p) {
     }
     __syncthreads();
 
-    // own cell of this thread in P3
-    const int tx = tid % TX, ty = tid / TX;
-    const int li = tx + 3, lj = ty + 3;
-    const int i = i0 + tx, j = j0 + ty;                     // logical cell
-    const bool active = (i <= Nx) && (j <= Ny);
-    const int gj = p.gj0 + j;                               // global row (wall logic)
     double Gn0 = 0.0, Gn1 = 0.0, Gn2 = 0.0, Gn3 = 0.0;
+    double *s_sqBx = smem + L::o_dg, *s_sqBy = s_sqBx + YP * YR;   // DIAG only
+    (void)s_sqBx; (void)s_sqBy;
 
     if constexpr (FORM == 0) {
         // ================= VectorInvariant + Jacobian Lorentz ======================
-        double *s_z = smem + 4 * SZ, *s_ut = smem + 5 * SZ, *s_vt = smem + 6 * SZ, *s_K = smem + 7 * SZ;
-        double *s_Bx = smem + 8 * SZ, *s_By = smem + 9 * SZ;
-        double *s_Fxh = smem + 10 * SZ, *s_Fyh = smem + 11 * SZ, *s_FxA = smem + 12 * SZ, *s_FyA = smem + 13 * SZ;
+        double *s_z = smem + L::o_z, *s_ut = smem + L::o_ut, *s_vt = smem + L::o_vt;
+        double *s_K = smem + L::o_K, *s_Bx = smem + L::o_Bx, *s_By = smem + L::o_By;
+        double *s_Fxh = smem + L::o_Fxh, *s_FxA = smem + L::o_FxA, *s_Fyh = smem + L::o_Fyh, *s_FyA = smem + L::o_FyA;
+#define Zf(arr, a, b) arr[((b) - 1) * ZP + (a) - 1]
+#define Cc(arr, a, b) arr[((b) - 2) * CP + (a) - 2]
+#define FX(arr, a, b) arr[((b) - 3) * XP + (a) - 3]
+#define FY(arr, a, b) arr[((b) - 3) * YP + (a) - 3]
 
-        // ---- P1: derived staggered fields ------------------------------------------
-        for (int t = tid; t < (TX + 5) * (TY + 5); t += NT) {      // zeta, ℑy u, ℑx v at ffc
-            int a = 1 + t % (TX + 5), b = 1 + t / (TX + 5);
-            double vc = AT(s_v, a, b), vw = AT(s_v, a - 1, b), uc = AT(s_u, a, b), us = AT(s_u, a, b - 1);
-            AT(s_z, a, b) = DIVAZ((p.dy * vc - p.dy * vw) - (p.dx * uc - p.dx * us));
-            AT(s_ut, a, b) = 0.5 * (us + uc);
-            AT(s_vt, a, b) = 0.5 * (vw + vc);
-        }
-        for (int t = tid; t < (TX + 2) * (TY + 2); t += NT) {      // K, Bx, By at ccc
-            int a = 2 + t % (TX + 2), b = 2 + t / (TX + 2);
-            double u0 = AT(s_u, a, b), u1 = AT(s_u, a + 1, b), v0 = AT(s_v, a, b), v1 = AT(s_v, a, b + 1);
-            AT(s_K, a, b) = (0.5 * (u0 * u0 + u1 * u1) + 0.5 * (v0 * v0 + v1 * v1)) / 2.0;
-            double Ac = AT(s_A, a, b), hc = AT(s_h, a, b);
-            double dyA0 = DIVDY(Ac - AT(s_A, a, b - 1)), dyA1 = DIVDY(AT(s_A, a, b + 1) - Ac);
-            double dxA0 = DIVDX(Ac - AT(s_A, a - 1, b)), dxA1 = DIVDX(AT(s_A, a + 1, b) - Ac);
-#if SWMHD_STRICT
-            AT(s_Bx, a, b) = -(0.5 * (dyA0 + dyA1)) / hc;           // sw_mhd_jacobian_functions.jl:5-7
-            AT(s_By, a, b) = (0.5 * (dxA0 + dxA1)) / hc;            // :1-3
-#else
-            double rh = frcp(hc);
-            AT(s_Bx, a, b) = -(0.5 * (dyA0 + dyA1)) * rh;
-            AT(s_By, a, b) = (0.5 * (dxA0 + dxA1)) * rh;
-#endif
-        }
-        __syncthreads();
-
-        // ---- P2: mass and tracer face fluxes, each face once -------------------------
-        constexpr int NXF = (TX + 1) * TY, NYF = TX * (TY + 1);
-        for (int t = tid; t < NXF + NYF; t += NT) {
-            if (t < NXF) {                                          // x-face (fcc)
-                int a = 3 + t % (TX + 1), b = 3 + t / (TX + 1);
-                double vel = AT(s_u, a, b);
-                AT(s_Fxh, a, b) = p.dy * upwind_weno_x(s_h, a, b, vel, eps);
-                AT(s_FxA, a, b) = p.dy * upwind_weno_x(s_A, a, b, vel, eps);
-            } else {                                                // y-face (cfc)
+        // ---- P1: one task list (heavy face fluxes first, light derived fields after) -----
+        constexpr int NXF = XP * XR, NYF = YP * YR, NZ = ZP * ZR, NC = CP * CR;
+        constexpr int NDG = DIAG ? NDG_ : 0;
+        for (int t = tid; t < NXF + NYF + NZ + NC + NDG; t += NT) {
+            if (t < NXF) {                                          // x-face (fcc): mass and tracer flux
+                int a = 3 + t % XP, b = 3 + t / XP;
+                double vel = RAW(s_u, a, b);
+                FX(s_Fxh, a, b) = p.dy * upwind_weno(&RAW(s_h, a, b), 1, vel, eps);
+                FX(s_FxA, a, b) = p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps);
+            } else if (t < NXF + NYF) {                             // y-face (cfc)
                 int q = t - NXF;
-                int a = 3 + q % TX, b = 3 + q / TX;
-                double vel = AT(s_v, a, b);
+                int a = 3 + q % YP, b = 3 + q / YP;
+                double vel = RAW(s_v, a, b);
                 bool buf = ybuf(p.by, p.gj0 + j0 + (b - 3), 3, p.NyG);
-                AT(s_Fyh, a, b) = p.dx * upwind_weno_y(s_h, a, b, vel, eps, buf);
-                AT(s_FyA, a, b) = p.dx * upwind_weno_y(s_A, a, b, vel, eps, buf);
+                FY(s_Fyh, a, b) = p.dx * upwind_weno_buf(&RAW(s_h, a, b), W, vel, eps, buf);
+                FY(s_FyA, a, b) = p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, buf);
+            } else if (t < NXF + NYF + NZ) {                        // zeta, ℑy u, ℑx v at ffc
+                int q = t - NXF - NYF;
+                int a = 1 + q % ZP, b = 1 + q / ZP;
+                double vc = RAW(s_v, a, b), vw = RAW(s_v, a - 1, b), uc = RAW(s_u, a, b), us = RAW(s_u, a, b - 1);
+#if SWMHD_STRICT
+                Zf(s_z, a, b) = DIVAZ((p.dy * vc - p.dy * vw) - (p.dx * uc - p.dx * us));
+#else
+                Zf(s_z, a, b) = fma(vc - vw, p.rdx, (us - uc) * p.rdy);
+#endif
+                Zf(s_ut, a, b) = 0.5 * (us + uc);
+                Zf(s_vt, a, b) = 0.5 * (vw + vc);
+            } else if (t < NXF + NYF + NZ + NC) {                   // K, Bx, By at ccc
+                int q = t - NXF - NYF - NZ;
+                int a = 2 + q % CP, b = 2 + q / CP;
+                double u0 = RAW(s_u, a, b), u1 = RAW(s_u, a + 1, b), v0 = RAW(s_v, a, b), v1 = RAW(s_v, a, b + 1);
+                double hc = RAW(s_h, a, b);
+#if SWMHD_STRICT
+                Cc(s_K, a, b) = (0.5 * (u0 * u0 + u1 * u1) + 0.5 * (v0 * v0 + v1 * v1)) / 2.0;
+                double Ac = RAW(s_A, a, b);
+                double dyA0 = DIVDY(Ac - RAW(s_A, a, b - 1)), dyA1 = DIVDY(RAW(s_A, a, b + 1) - Ac);
+                double dxA0 = DIVDX(Ac - RAW(s_A, a - 1, b)), dxA1 = DIVDX(RAW(s_A, a + 1, b) - Ac);
+                Cc(s_Bx, a, b) = -(0.5 * (dyA0 + dyA1)) / hc;       // sw_mhd_jacobian_functions.jl:5-7
+                Cc(s_By, a, b) = (0.5 * (dxA0 + dxA1)) / hc;        // :1-3
+#else
+                Cc(s_K, a, b) = 0.25 * (fma(u0, u0, u1 * u1) + fma(v0, v0, v1 * v1));
+                double rh = frcp(hc);
+                Cc(s_Bx, a, b) = ((RAW(s_A, a, b - 1) - RAW(s_A, a, b + 1)) * (0.5 * p.rdy)) * rh;
+                Cc(s_By, a, b) = ((RAW(s_A, a + 1, b) - RAW(s_A, a - 1, b)) * (0.5 * p.rdx)) * rh;
+#endif
+            } else if constexpr (DIAG) {                            // diagnostic B^2 at faces
+                int q = t - NXF - NYF - NZ - NC;
+                if (q < YP * YR) {                                  // (dyA / ℑy h)^2 at cfc, a in [3,TX+2], b in [3,TY+3]
+                    int a = 3 + q % YP, b = 3 + q / YP;
+                    double bx = fdiv(-DIVDY(RAW(s_A, a, b) - RAW(s_A, a, b - 1)), 0.5 * (RAW(s_h, a, b - 1) + RAW(s_h, a, b)));
+                    s_sqBx[q] = bx * bx;
+                } else {                                            // (dxA / ℑx h)^2 at fcc, a in [3,TX+3], b in [2,TY+3]
+                    int r = q - YP * YR;
+                    int a = 3 + r % XP, b = 2 + r / XP;
+                    double by_ = fdiv(DIVDX(RAW(s_A, a, b) - RAW(s_A, a - 1, b)), 0.5 * (RAW(s_h, a - 1, b) + RAW(s_h, a, b)));
+                    s_sqBy[r] = by_ * by_;
+                }
             }
         }
         __syncthreads();
 
-        // ---- P3: tendencies of the own cell -------------------------------------------
+        // ---- P2: tendencies of the own cell -------------------------------------------
         if (active) {
             // Gu at fcc
             {
-                double vhat = 0.5 * (0.5 * (AT(s_v, li - 1, lj) + AT(s_v, li, lj)) +
-                                     0.5 * (AT(s_v, li - 1, lj + 1) + AT(s_v, li, lj + 1)));
+                double vhat = avg4(RAW(s_v, li - 1, lj), RAW(s_v, li, lj), RAW(s_v, li - 1, lj + 1), RAW(s_v, li, lj + 1));
                 const int lf = lj + 1;                              // zeta along y to centre j
                 double adv;
                 if (ybuf(p.by, gj + 1, 3, p.NyG + 1)) {
-                    adv = vhat * sym2(AT(s_z, li, lf - 1), AT(s_z, li, lf));
+                    adv = vhat * sym2(Zf(s_z, li, lf - 1), Zf(s_z, li, lf));
                 } else {
                     const bool pos = vhat > 0.0;
-                    adv = vhat * upwind_weno_vs(s_z, s_ut, s_vt, (pos ? lf - 3 : lf + 2) * W + li, pos ? W : -W, eps);
+                    const int off = ((pos ? lf - 3 : lf + 2) - 1) * ZP + li - 1;
+                    adv = vhat * weno5_vs(s_z + off, s_ut + off, s_vt + off, pos ? ZP : -ZP, eps);
                 }
-                double dK = DIVDX(AT(s_K, li, lj) - AT(s_K, li - 1, lj));
-                double pg = p.g * DIVDX(AT(s_h, li, lj) - AT(s_h, li - 1, lj));
+                double dK = DIVDX(Cc(s_K, li, lj) - Cc(s_K, li - 1, lj));
+                double pg = p.g * DIVDX(RAW(s_h, li, lj) - RAW(s_h, li - 1, lj));
                 // lorentz_force_func_x — sw_mhd_jacobian_functions.jl:10-13,20-22
-                double dxA = DIVDX(AT(s_A, li, lj) - AT(s_A, li - 1, lj));
-#define DYBX(a, b) DIVDY(AT(s_Bx, a, b) - AT(s_Bx, a, (b) - 1))
-#define DYA(a, b) DIVDY(AT(s_A, a, b) - AT(s_A, a, (b) - 1))
-                double m1 = 0.5 * (0.5 * (DYBX(li - 1, lj) + DYBX(li, lj)) + 0.5 * (DYBX(li - 1, lj + 1) + DYBX(li, lj + 1)));
-                double m2 = 0.5 * (0.5 * (DYA(li - 1, lj) + DYA(li, lj)) + 0.5 * (DYA(li - 1, lj + 1) + DYA(li, lj + 1)));
-                double jac = dxA * m1 - m2 * DIVDX(AT(s_Bx, li, lj) - AT(s_Bx, li - 1, lj));
-                double hx = 0.5 * (AT(s_h, li - 1, lj) + AT(s_h, li, lj));
+                double dxA = DIVDX(RAW(s_A, li, lj) - RAW(s_A, li - 1, lj));
+                double hx = 0.5 * (RAW(s_h, li - 1, lj) + RAW(s_h, li, lj));
+#if SWMHD_STRICT
+#define DYBX(a, b) DIVDY(Cc(s_Bx, a, b) - Cc(s_Bx, a, (b) - 1))
+#define DYA(a, b) DIVDY(RAW(s_A, a, b) - RAW(s_A, a, (b) - 1))
+                double m1 = avg4(DYBX(li - 1, lj), DYBX(li, lj), DYBX(li - 1, lj + 1), DYBX(li, lj + 1));
+                double m2 = avg4(DYA(li - 1, lj), DYA(li, lj), DYA(li - 1, lj + 1), DYA(li, lj + 1));
+                double jac = dxA * m1 - m2 * DIVDX(Cc(s_Bx, li, lj) - Cc(s_Bx, li - 1, lj));
                 double lor = fdiv(1.0, hx) * jac;
                 Gn0 = (((adv - dK) - pg) + p.f * vhat) + lor;
+#else
+                // ℑxy(∂y F) telescopes to (F(i-1,j+1) + F(i,j+1) - F(i-1,j-1) - F(i,j-1)) / (4 dy)
+                double m1 = ((Cc(s_Bx, li - 1, lj + 1) + Cc(s_Bx, li, lj + 1)) - (Cc(s_Bx, li - 1, lj - 1) + Cc(s_Bx, li, lj - 1))) * (0.25 * p.rdy);
+                double m2 = ((RAW(s_A, li - 1, lj + 1) + RAW(s_A, li, lj + 1)) - (RAW(s_A, li - 1, lj - 1) + RAW(s_A, li, lj - 1))) * (0.25 * p.rdy);
+                double jac = fma(dxA, m1, -(m2 * ((Cc(s_Bx, li, lj) - Cc(s_Bx, li - 1, lj)) * p.rdx)));
+                Gn0 = fma(jac, frcp(hx), fma(p.f, vhat, (adv - dK) - pg));
+#endif
             }
             // Gv at cfc (wall rows of a Bounded-y grid keep v = 0)
             if (!(p.by && gj < 2)) {
-                double uhat = 0.5 * (0.5 * (AT(s_u, li, lj - 1) + AT(s_u, li + 1, lj - 1)) +
-                                     0.5 * (AT(s_u, li, lj) + AT(s_u, li + 1, lj)));
+                double uhat = avg4(RAW(s_u, li, lj - 1), RAW(s_u, li + 1, lj - 1), RAW(s_u, li, lj), RAW(s_u, li + 1, lj));
                 const int lf = li + 1;                              // zeta along x to centre i
                 const bool pos = uhat > 0.0;
-                double adv = uhat * upwind_weno_vs(s_z, s_ut, s_vt, lj * W + (pos ? lf - 3 : lf + 2), pos ? 1 : -1, eps);
-                double dK = DIVDY(AT(s_K, li, lj) - AT(s_K, li, lj - 1));
-                double pg = p.g * DIVDY(AT(s_h, li, lj) - AT(s_h, li, lj - 1));
+                const int off = (lj - 1) * ZP + (pos ? lf - 3 : lf + 2) - 1;
+                double adv = uhat * weno5_vs(s_z + off, s_ut + off, s_vt + off, pos ? 1 : -1, eps);
+                double dK = DIVDY(Cc(s_K, li, lj) - Cc(s_K, li, lj - 1));
+                double pg = p.g * DIVDY(RAW(s_h, li, lj) - RAW(s_h, li, lj - 1));
                 // lorentz_force_func_y — sw_mhd_jacobian_functions.jl:15-18,24-26
-#define DXA(a, b) DIVDX(AT(s_A, a, b) - AT(s_A, (a) - 1, b))
-#define DXBY(a, b) DIVDX(AT(s_By, a, b) - AT(s_By, (a) - 1, b))
-                double m1 = 0.5 * (0.5 * (DXA(li, lj - 1) + DXA(li + 1, lj - 1)) + 0.5 * (DXA(li, lj) + DXA(li + 1, lj)));
-                double m2 = 0.5 * (0.5 * (DXBY(li, lj - 1) + DXBY(li + 1, lj - 1)) + 0.5 * (DXBY(li, lj) + DXBY(li + 1, lj)));
-                double jac = m1 * DIVDY(AT(s_By, li, lj) - AT(s_By, li, lj - 1)) - DYA(li, lj) * m2;
-                double hy = 0.5 * (AT(s_h, li, lj - 1) + AT(s_h, li, lj));
+                double dyA = DIVDY(RAW(s_A, li, lj) - RAW(s_A, li, lj - 1));
+                double hy = 0.5 * (RAW(s_h, li, lj - 1) + RAW(s_h, li, lj));
+#if SWMHD_STRICT
+#define DXA(a, b) DIVDX(RAW(s_A, a, b) - RAW(s_A, (a) - 1, b))
+#define DXBY(a, b) DIVDX(Cc(s_By, a, b) - Cc(s_By, (a) - 1, b))
+                double m1 = avg4(DXA(li, lj - 1), DXA(li + 1, lj - 1), DXA(li, lj), DXA(li + 1, lj));
+                double m2 = avg4(DXBY(li, lj - 1), DXBY(li + 1, lj - 1), DXBY(li, lj), DXBY(li + 1, lj));
+                double jac = m1 * DIVDY(Cc(s_By, li, lj) - Cc(s_By, li, lj - 1)) - dyA * m2;
                 double lor = fdiv(1.0, hy) * jac;
                 Gn1 = (((-adv - dK) - pg) - p.f * uhat) + lor;
+#else
+                double m1 = ((RAW(s_A, li + 1, lj - 1) + RAW(s_A, li + 1, lj)) - (RAW(s_A, li - 1, lj - 1) + RAW(s_A, li - 1, lj))) * (0.25 * p.rdx);
+                double m2 = ((Cc(s_By, li + 1, lj - 1) + Cc(s_By, li + 1, lj)) - (Cc(s_By, li - 1, lj - 1) + Cc(s_By, li - 1, lj))) * (0.25 * p.rdx);
+                double jac = fma(m1, (Cc(s_By, li, lj) - Cc(s_By, li, lj - 1)) * p.rdy, -(dyA * m2));
+                Gn1 = fma(jac, frcp(hy), fma(-p.f, uhat, (-adv - dK) - pg));
+#endif
             }
             // Gh, GA at ccc
             {
-                Gn2 = -(p.inv_az * ((AT(s_Fxh, li + 1, lj) - AT(s_Fxh, li, lj)) + (AT(s_Fyh, li, lj + 1) - AT(s_Fyh, li, lj))));
-                double d = p.inv_az * ((AT(s_FxA, li + 1, lj) - AT(s_FxA, li, lj)) + (AT(s_FyA, li, lj + 1) - AT(s_FyA, li, lj)));
-                double dv = p.inv_az * ((p.dy * AT(s_u, li + 1, lj) - p.dy * AT(s_u, li, lj)) +
-                                        (p.dx * AT(s_v, li, lj + 1) - p.dx * AT(s_v, li, lj)));
-                Gn3 = -d + AT(s_A, li, lj) * dv;
+                Gn2 = -(p.inv_az * ((FX(s_Fxh, li + 1, lj) - FX(s_Fxh, li, lj)) + (FY(s_Fyh, li, lj + 1) - FY(s_Fyh, li, lj))));
+                double d = p.inv_az * ((FX(s_FxA, li + 1, lj) - FX(s_FxA, li, lj)) + (FY(s_FyA, li, lj + 1) - FY(s_FyA, li, lj)));
+#if SWMHD_STRICT
+                double dv = p.inv_az * ((p.dy * RAW(s_u, li + 1, lj) - p.dy * RAW(s_u, li, lj)) +
+                                        (p.dx * RAW(s_v, li, lj + 1) - p.dx * RAW(s_v, li, lj)));
+#else
+                double dv = fma(RAW(s_u, li + 1, lj) - RAW(s_u, li, lj), p.rdx, (RAW(s_v, li, lj + 1) - RAW(s_v, li, lj)) * p.rdy);
+#endif
+                Gn3 = -d + RAW(s_A, li, lj) * dv;
             }
         }
     } else {
         // ================= Conservative + divergence-form Lorentz ====================
-        double *s_hBx = smem + 4 * SZ, *s_hBy = smem + 5 * SZ, *s_Bx = smem + 6 * SZ, *s_By = smem + 7 * SZ;
-        double *s_hff = smem + 8 * SZ;
-        double *s_Fuu = smem + 9 * SZ, *s_Fvu = smem + 10 * SZ, *s_Fuv = smem + 11 * SZ, *s_Fvv = smem + 12 * SZ;
-        double *s_Lxx = smem + 13 * SZ, *s_Lyx = smem + 14 * SZ, *s_Lxy = smem + 15 * SZ, *s_Lyy = smem + 16 * SZ;
-        double *s_Tx = smem + 17 * SZ, *s_Ty = smem + 18 * SZ, *s_uq = smem + 19 * SZ, *s_vq = smem + 20 * SZ;
-        double *s_hx = smem + 21 * SZ, *s_hy = smem + 22 * SZ;
-        const int NxG = Nx; (void)NxG;
+        double *s_hBx = smem + L::o_hBx, *s_hBy = smem + L::o_hBy, *s_Bx = smem + L::o_Bx, *s_By = smem + L::o_By;
+        double *s_hx = smem + L::o_hx, *s_hy = smem + L::o_hy, *s_hff = smem + L::o_hff;
+        double *s_Fuu = smem + L::o_Fuu, *s_Lxx = smem + L::o_Lxx, *s_Fuv = smem + L::o_Fuv, *s_Lxy = smem + L::o_Lxy;
+        double *s_Tx = smem + L::o_Tx, *s_uq = smem + L::o_uq;
+        double *s_Fvu = smem + L::o_Fvu, *s_Lyx = smem + L::o_Lyx, *s_Fvv = smem + L::o_Fvv, *s_Lyy = smem + L::o_Lyy;
+        double *s_Ty = smem + L::o_Ty, *s_vq = smem + L::o_vq;
+#define Bf(arr, a, b) arr[((b) - 1) * BP + (a) - 1]
+#define HF(a, b) s_hff[((b) - 3) * XP + (a) - 3]
+#define FXc(arr, a, b) arr[((b) - 3) * XP + (a) - 2]   /* ccc x-type: a in [2,TX+2] */
+#define FX3(arr, a, b) arr[((b) - 3) * XP + (a) - 3]   /* a in [3,TX+3], b in [3,TY+2] */
+#define FY3(arr, a, b) arr[((b) - 3) * YP + (a) - 3]   /* a in [3,TX+2], b in [3,TY+3] */
+#define FYc(arr, a, b) arr[((b) - 2) * YP + (a) - 3]   /* ccc y-type: b in [2,TY+2] */
 
-        // ---- P1: hBx, hBy, Bx, By (sw_mhd_divergence_functions.jl:134-148), ℑ h ----------
-        for (int t = tid; t < (TX + 4) * (TY + 4); t += NT) {
-            int a = 1 + t % (TX + 4), b = 1 + t / (TX + 4);
-#define DYA(a_, b_) DIVDY(AT(s_A, a_, b_) - AT(s_A, a_, (b_) - 1))
-#define DXA(a_, b_) DIVDX(AT(s_A, a_, b_) - AT(s_A, (a_) - 1, b_))
-            double hbx = -(0.5 * (0.5 * (DYA(a - 1, b) + DYA(a, b)) + 0.5 * (DYA(a - 1, b + 1) + DYA(a, b + 1))));
-            double hby = 0.5 * (0.5 * (DXA(a, b - 1) + DXA(a + 1, b - 1)) + 0.5 * (DXA(a, b) + DXA(a + 1, b)));
-            double hx = 0.5 * (AT(s_h, a - 1, b) + AT(s_h, a, b));
-            double hy = 0.5 * (AT(s_h, a, b - 1) + AT(s_h, a, b));
-            AT(s_hBx, a, b) = hbx; AT(s_hBy, a, b) = hby;
-            AT(s_hx, a, b) = hx;   AT(s_hy, a, b) = hy;
-            AT(s_Bx, a, b) = fdiv(hbx, hx);
-            AT(s_By, a, b) = fdiv(hby, hy);
-        }
-        for (int t = tid; t < (TX + 1) * (TY + 1); t += NT) {      // ℑxyᶠᶠᵃ h
-            int a = 3 + t % (TX + 1), b = 3 + t / (TX + 1);
-            AT(s_hff, a, b) = 0.5 * (0.5 * (AT(s_h, a - 1, b - 1) + AT(s_h, a, b - 1)) + 0.5 * (AT(s_h, a - 1, b) + AT(s_h, a, b)));
-        }
-        __syncthreads();
-
-        // ---- P2: every flux once -------------------------------------------------------
-        constexpr int NXF = (TX + 1) * TY, NYF = TX * (TY + 1);
-        const int NyG = p.NyG, by = p.by;
-        for (int t = tid; t < 3 * NXF + 3 * NYF; t += NT) {
-            if (t < NXF) {                      // ccc (i0-1..i0+TX-1, j): F_uu and Lxx
-                int a = 2 + t % (TX + 1), b = 3 + t / (TX + 1);
-                double ut = sym4(AT(s_u, a - 1, b), AT(s_u, a, b), AT(s_u, a + 1, b), AT(s_u, a + 2, b));
-                AT(s_Fuu, a, b) = fdiv(p.dy * upwind_weno_x(s_u, a + 1, b, ut, eps), AT(s_h, a, b));
-                // advective_lorentz_flux_hBx_bx :38-60 (x periodic: final else branch)
-                double ul = 0.5 * (AT(s_hBx, a, b) + AT(s_hBx, a + 1, b));
-                double L = third(AT(s_Bx, a + 1, b), AT(s_Bx, a, b), AT(s_Bx, a - 1, b));
-                double R = thirdR(AT(s_Bx, a + 2, b), AT(s_Bx, a + 1, b), AT(s_Bx, a, b));
-                AT(s_Lxx, a, b) = p.dy * upwind_sel(ul, L, R);
-            } else if (t < 2 * NXF) {           // ffc (i0..i0+TX, j): F_uv and Lxy
-                int q = t - NXF;
-                int a = 3 + q % (TX + 1), b = 3 + q / (TX + 1);
-                int gjf = p.gj0 + j0 + (b - 3);
-                double ut = ybuf(by, gjf, 2, NyG) ? sym2(AT(s_u, a, b - 1), AT(s_u, a, b))
-                                                  : sym4(AT(s_u, a, b - 2), AT(s_u, a, b - 1), AT(s_u, a, b), AT(s_u, a, b + 1));
-                AT(s_Fuv, a, b) = fdiv(p.dy * upwind_weno_x(s_v, a, b, ut, eps), AT(s_hff, a, b));
-                // advective_lorentz_flux_hBx_by :86-108
-                double ul = 0.5 * (AT(s_hBx, a, b - 1) + AT(s_hBx, a, b));
-                double L = third(AT(s_By, a, b), AT(s_By, a - 1, b), AT(s_By, a - 2, b));
-                double R = thirdR(AT(s_By, a + 1, b), AT(s_By, a, b), AT(s_By, a - 1, b));
-                AT(s_Lxy, a, b) = p.dy * upwind_sel(ul, L, R);
-            } else if (t < 3 * NXF) {           // fcc (i0..i0+TX, j): tracer transport flux, uh/ℑx h
-                int q = t - 2 * NXF;
-                int a = 3 + q % (TX + 1), b = 3 + q / (TX + 1);
-                double vel = AT(s_u, a, b), hx = AT(s_hx, a, b);
-                AT(s_Tx, a, b) = fdiv(p.dy * upwind_weno_x(s_A, a, b, vel, eps), hx);
-                AT(s_uq, a, b) = fdiv(vel, hx);
-            } else if (t < 3 * NXF + NYF) {     // ffc (i, j0..j0+TY): F_vu and Lyx
-                int q = t - 3 * NXF;
-                int a = 3 + q % TX, b = 3 + q / TX;
-                int gjf = p.gj0 + j0 + (b - 3);
-                double vt = sym4(AT(s_v, a - 2, b), AT(s_v, a - 1, b), AT(s_v, a, b), AT(s_v, a + 1, b));
-                AT(s_Fvu, a, b) = fdiv(p.dx * upwind_weno_y(s_u, a, b, vt, eps, ybuf(by, gjf, 3, NyG)), AT(s_hff, a, b));
-                // advective_lorentz_flux_hBy_bx :62-84 with its Bounded-y edge branches
-                double vl = 0.5 * (AT(s_hBy, a - 1, b) + AT(s_hBy, a, b));
-                double L3 = third(AT(s_Bx, a, b), AT(s_Bx, a, b - 1), AT(s_Bx, a, b - 2));
-                double R3 = thirdR(AT(s_Bx, a, b + 1), AT(s_Bx, a, b), AT(s_Bx, a, b - 1));
-                double L1 = AT(s_Bx, a, b - 1), R1 = AT(s_Bx, a, b);
-                double L = L3, R = R3;
-                if (by) {
-                    if (gjf == 1) { L = R1; R = R1; } else if (gjf == 2) { L = L1; R = R3; }
-                    else if (gjf == NyG) { L = L3; R = R1; } else if (gjf == NyG + 1) { L = L1; R = L1; }
-                }
-                AT(s_Lyx, a, b) = p.dx * upwind_sel(vl, L, R);
-            } else if (t < 3 * NXF + 2 * NYF) { // ccc (i, j0-1..j0+TY-1): F_vv and Lyy
-                int q = t - 3 * NXF - NYF;
-                int a = 3 + q % TX, b = 2 + q / TX;
-                int gjc = p.gj0 + j0 + (b - 3);                     // global cell row
-                double vt = ybuf(by, gjc + 1, 2, NyG + 1) ? sym2(AT(s_v, a, b), AT(s_v, a, b + 1))
-                                                          : sym4(AT(s_v, a, b - 1), AT(s_v, a, b), AT(s_v, a, b + 1), AT(s_v, a, b + 2));
-                AT(s_Fvv, a, b) = fdiv(p.dx * upwind_weno_y(s_v, a, b + 1, vt, eps, ybuf(by, gjc + 1, 3, NyG + 1)), AT(s_h, a, b));
-                // advective_lorentz_flux_hBy_by :110-132
-                double vl = 0.5 * (AT(s_hBy, a, b) + AT(s_hBy, a, b + 1));
-                double L3 = third(AT(s_By, a, b + 1), AT(s_By, a, b), AT(s_By, a, b - 1));
-                double R3 = thirdR(AT(s_By, a, b + 2), AT(s_By, a, b + 1), AT(s_By, a, b));
-                double L1 = AT(s_By, a, b), R1 = AT(s_By, a, b + 1);
-                double L = L3, R = R3;
-                if (by) {
-                    if (gjc == 0) { L = R1; R = R1; } else if (gjc == 1) { L = L1; R = R3; }
-                    else if (gjc == NyG - 1) { L = L3; R = R1; } else if (gjc == NyG) { L = L1; R = L1; }
-                }
-                AT(s_Lyy, a, b) = p.dx * upwind_sel(vl, L, R);
-            } else {                            // cfc (i, j0..j0+TY): tracer transport flux, vh/ℑy h
-                int q = t - 3 * NXF - 2 * NYF;
-                int a = 3 + q % TX, b = 3 + q / TX;
-                int gjf = p.gj0 + j0 + (b - 3);
-                double vel = AT(s_v, a, b), hy = AT(s_hy, a, b);
-                AT(s_Ty, a, b) = fdiv(p.dx * upwind_weno_y(s_A, a, b, vel, eps, ybuf(by, gjf, 3, NyG)), hy);
-                AT(s_vq, a, b) = fdiv(vel, hy);
+        // ---- P1a: hBx, hBy, Bx, By (sw_mhd_divergence_functions.jl:134-148), face and corner h ----
+        for (int t = tid; t < BP * BR + XP * YR; t += NT) {
+            if (t < BP * BR) {
+                int a = 1 + t % BP, b = 1 + t / BP;
+#if SWMHD_STRICT
+#define DYA_(a_, b_) DIVDY(RAW(s_A, a_, b_) - RAW(s_A, a_, (b_) - 1))
+#define DXA_(a_, b_) DIVDX(RAW(s_A, a_, b_) - RAW(s_A, (a_) - 1, b_))
+                double hbx = -avg4(DYA_(a - 1, b), DYA_(a, b), DYA_(a - 1, b + 1), DYA_(a, b + 1));
+                double hby = avg4(DXA_(a, b - 1), DXA_(a + 1, b - 1), DXA_(a, b), DXA_(a + 1, b));
+#else
+                double hbx = ((RAW(s_A, a - 1, b - 1) + RAW(s_A, a, b - 1)) - (RAW(s_A, a - 1, b + 1) + RAW(s_A, a, b + 1))) * (0.25 * p.rdy);
+                double hby = ((RAW(s_A, a + 1, b - 1) + RAW(s_A, a + 1, b)) - (RAW(s_A, a - 1, b - 1) + RAW(s_A, a - 1, b))) * (0.25 * p.rdx);
+#endif
+                double hx = 0.5 * (RAW(s_h, a - 1, b) + RAW(s_h, a, b));
+                double hy = 0.5 * (RAW(s_h, a, b - 1) + RAW(s_h, a, b));
+                Bf(s_hBx, a, b) = hbx; Bf(s_hBy, a, b) = hby;
+                Bf(s_hx, a, b) = hx;   Bf(s_hy, a, b) = hy;
+                Bf(s_Bx, a, b) = fdiv(hbx, hx);
+                Bf(s_By, a, b) = fdiv(hby, hy);
+            } else {                                                // ℑxyᶠᶠᵃ h, a in [3,TX+3], b in [3,TY+3]
+                int q = t - BP * BR;
+                int a = 3 + q % XP, b = 3 + q / XP;
+                HF(a, b) = avg4(RAW(s_h, a - 1, b - 1), RAW(s_h, a, b - 1), RAW(s_h, a - 1, b), RAW(s_h, a, b));
             }
         }
         __syncthreads();
 
-        // ---- P3 --------------------------------------------------------------------------
+        // ---- P1b: every flux once --------------------------------------------------------
+        constexpr int NXF = XP * XR, NYF = YP * YR;
+        constexpr int NDG = DIAG ? NDG_ : 0;
+        const int NyG = p.NyG, by = p.by;
+        for (int t = tid; t < 3 * NXF + 3 * NYF + NDG; t += NT) {
+            if (t < NXF) {                      // ccc (i0-1..i0+TX-1, j): F_uu and Lxx
+                int a = 2 + t % XP, b = 3 + t / XP;
+                double ut = sym4(RAW(s_u, a - 1, b), RAW(s_u, a, b), RAW(s_u, a + 1, b), RAW(s_u, a + 2, b));
+                FXc(s_Fuu, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_u, a + 1, b), 1, ut, eps), RAW(s_h, a, b));
+                // advective_lorentz_flux_hBx_bx :38-60 (x periodic: final else branch)
+                double ul = 0.5 * (Bf(s_hBx, a, b) + Bf(s_hBx, a + 1, b));
+                double Lq = third(Bf(s_Bx, a + 1, b), Bf(s_Bx, a, b), Bf(s_Bx, a - 1, b));
+                double Rq = thirdR(Bf(s_Bx, a + 2, b), Bf(s_Bx, a + 1, b), Bf(s_Bx, a, b));
+                FXc(s_Lxx, a, b) = p.dy * upwind_sel(ul, Lq, Rq);
+            } else if (t < 2 * NXF) {           // ffc (i0..i0+TX, j): F_uv and Lxy
+                int q = t - NXF;
+                int a = 3 + q % XP, b = 3 + q / XP;
+                int gjf = p.gj0 + j0 + (b - 3);
+                double ut = ybuf(by, gjf, 2, NyG) ? sym2(RAW(s_u, a, b - 1), RAW(s_u, a, b))
+                                                  : sym4(RAW(s_u, a, b - 2), RAW(s_u, a, b - 1), RAW(s_u, a, b), RAW(s_u, a, b + 1));
+                FX3(s_Fuv, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_v, a, b), 1, ut, eps), HF(a, b));
+                // advective_lorentz_flux_hBx_by :86-108
+                double ul = 0.5 * (Bf(s_hBx, a, b - 1) + Bf(s_hBx, a, b));
+                double Lq = third(Bf(s_By, a, b), Bf(s_By, a - 1, b), Bf(s_By, a - 2, b));
+                double Rq = thirdR(Bf(s_By, a + 1, b), Bf(s_By, a, b), Bf(s_By, a - 1, b));
+                FX3(s_Lxy, a, b) = p.dy * upwind_sel(ul, Lq, Rq);
+            } else if (t < 3 * NXF) {           // fcc (i0..i0+TX, j): tracer transport flux, uh/ℑx h
+                int q = t - 2 * NXF;
+                int a = 3 + q % XP, b = 3 + q / XP;
+                double vel = RAW(s_u, a, b), hx = Bf(s_hx, a, b);
+#if SWMHD_STRICT
+                FX3(s_Tx, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps), hx);
+                FX3(s_uq, a, b) = fdiv(vel, hx);
+#else
+                double rhx = frcp(hx);
+                FX3(s_Tx, a, b) = (p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps)) * rhx;
+                FX3(s_uq, a, b) = vel * rhx;
+#endif
+            } else if (t < 3 * NXF + NYF) {     // ffc (i, j0..j0+TY): F_vu and Lyx
+                int q = t - 3 * NXF;
+                int a = 3 + q % YP, b = 3 + q / YP;
+                int gjf = p.gj0 + j0 + (b - 3);
+                double vt = sym4(RAW(s_v, a - 2, b), RAW(s_v, a - 1, b), RAW(s_v, a, b), RAW(s_v, a + 1, b));
+                FY3(s_Fvu, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_u, a, b), W, vt, eps, ybuf(by, gjf, 3, NyG)), HF(a, b));
+                // advective_lorentz_flux_hBy_bx :62-84 with its Bounded-y edge branches
+                double vl = 0.5 * (Bf(s_hBy, a - 1, b) + Bf(s_hBy, a, b));
+                double L3 = third(Bf(s_Bx, a, b), Bf(s_Bx, a, b - 1), Bf(s_Bx, a, b - 2));
+                double R3 = thirdR(Bf(s_Bx, a, b + 1), Bf(s_Bx, a, b), Bf(s_Bx, a, b - 1));
+                double L1 = Bf(s_Bx, a, b - 1), R1 = Bf(s_Bx, a, b);
+                double Lq = L3, Rq = R3;
+                if (by) {
+                    if (gjf == 1) { Lq = R1; Rq = R1; } else if (gjf == 2) { Lq = L1; Rq = R3; }
+                    else if (gjf == NyG) { Lq = L3; Rq = R1; } else if (gjf == NyG + 1) { Lq = L1; Rq = L1; }
+                }
+                FY3(s_Lyx, a, b) = p.dx * upwind_sel(vl, Lq, Rq);
+            } else if (t < 3 * NXF + 2 * NYF) { // ccc (i, j0-1..j0+TY-1): F_vv and Lyy
+                int q = t - 3 * NXF - NYF;
+                int a = 3 + q % YP, b = 2 + q / YP;
+                int gjc = p.gj0 + j0 + (b - 3);                     // global cell row
+                double vt = ybuf(by, gjc + 1, 2, NyG + 1) ? sym2(RAW(s_v, a, b), RAW(s_v, a, b + 1))
+                                                          : sym4(RAW(s_v, a, b - 1), RAW(s_v, a, b), RAW(s_v, a, b + 1), RAW(s_v, a, b + 2));
+                FYc(s_Fvv, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_v, a, b + 1), W, vt, eps, ybuf(by, gjc + 1, 3, NyG + 1)), RAW(s_h, a, b));
+                // advective_lorentz_flux_hBy_by :110-132
+                double vl = 0.5 * (Bf(s_hBy, a, b) + Bf(s_hBy, a, b + 1));
+                double L3 = third(Bf(s_By, a, b + 1), Bf(s_By, a, b), Bf(s_By, a, b - 1));
+                double R3 = thirdR(Bf(s_By, a, b + 2), Bf(s_By, a, b + 1), Bf(s_By, a, b));
+                double L1 = Bf(s_By, a, b), R1 = Bf(s_By, a, b + 1);
+                double Lq = L3, Rq = R3;
+                if (by) {
+                    if (gjc == 0) { Lq = R1; Rq = R1; } else if (gjc == 1) { Lq = L1; Rq = R3; }
+                    else if (gjc == NyG - 1) { Lq = L3; Rq = R1; } else if (gjc == NyG) { Lq = L1; Rq = L1; }
+                }
+                FYc(s_Lyy, a, b) = p.dx * upwind_sel(vl, Lq, Rq);
+            } else if (t < 3 * NXF + 3 * NYF) { // cfc (i, j0..j0+TY): tracer transport flux, vh/ℑy h
+                int q = t - 3 * NXF - 2 * NYF;
+                int a = 3 + q % YP, b = 3 + q / YP;
+                int gjf = p.gj0 + j0 + (b - 3);
+                double vel = RAW(s_v, a, b), hy = Bf(s_hy, a, b);
+#if SWMHD_STRICT
+                FY3(s_Ty, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG)), hy);
+                FY3(s_vq, a, b) = fdiv(vel, hy);
+#else
+                double rhy = frcp(hy);
+                FY3(s_Ty, a, b) = (p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG))) * rhy;
+                FY3(s_vq, a, b) = vel * rhy;
+#endif
+            } else if constexpr (DIAG) {
+                int q = t - 3 * NXF - 3 * NYF;
+                if (q < YP * YR) {
+                    int a = 3 + q % YP, b = 3 + q / YP;
+                    double bx = fdiv(-DIVDY(RAW(s_A, a, b) - RAW(s_A, a, b - 1)), Bf(s_hy, a, b));
+                    s_sqBx[q] = bx * bx;
+                } else {
+                    int r = q - YP * YR;
+                    int a = 3 + r % XP, b = 2 + r / XP;
+                    double by_ = fdiv(DIVDX(RAW(s_A, a, b) - RAW(s_A, a - 1, b)), Bf(s_hx, a, b));
+                    s_sqBy[r] = by_ * by_;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- P2 --------------------------------------------------------------------------
         if (active) {
             // d(g h^2 / 2): h = 1 + O(1e-9) makes this a cancellation; keep the products
             // un-contracted (no FMA) in both arithmetic modes so the rounding is symmetric.
             const double hg = 0.5 * p.g;
-            double hc = AT(s_h, li, lj), hw = AT(s_h, li - 1, lj), hs = AT(s_h, li, lj - 1);
+            double hc = RAW(s_h, li, lj), hw = RAW(s_h, li - 1, lj), hs = RAW(s_h, li, lj - 1);
             double Pc = __dmul_rn(hg, __dmul_rn(hc, hc));
             double Pw = __dmul_rn(hg, __dmul_rn(hw, hw)), Ps = __dmul_rn(hg, __dmul_rn(hs, hs));
             {   // Guh
-                double dm = p.inv_az * ((AT(s_Fuu, li, lj) - AT(s_Fuu, li - 1, lj)) + (AT(s_Fvu, li, lj + 1) - AT(s_Fvu, li, lj)));
+                double dm = p.inv_az * ((FXc(s_Fuu, li, lj) - FXc(s_Fuu, li - 1, lj)) + (FY3(s_Fvu, li, lj + 1) - FY3(s_Fvu, li, lj)));
                 double pg = DIVDX(__dsub_rn(Pc, Pw));
-                double vhat = 0.5 * (0.5 * (AT(s_v, li - 1, lj) + AT(s_v, li, lj)) + 0.5 * (AT(s_v, li - 1, lj + 1) + AT(s_v, li, lj + 1)));
-                double lor = p.inv_az * ((AT(s_Lxx, li, lj) - AT(s_Lxx, li - 1, lj)) + (AT(s_Lyx, li, lj + 1) - AT(s_Lyx, li, lj)));
+                double vhat = avg4(RAW(s_v, li - 1, lj), RAW(s_v, li, lj), RAW(s_v, li - 1, lj + 1), RAW(s_v, li, lj + 1));
+                double lor = p.inv_az * ((FXc(s_Lxx, li, lj) - FXc(s_Lxx, li - 1, lj)) + (FY3(s_Lyx, li, lj + 1) - FY3(s_Lyx, li, lj)));
                 Gn0 = ((-dm - pg) + p.f * vhat) + lor;
             }
             if (!(p.by && gj < 2)) {   // Gvh
-                double dm = p.inv_az * ((AT(s_Fuv, li + 1, lj) - AT(s_Fuv, li, lj)) + (AT(s_Fvv, li, lj) - AT(s_Fvv, li, lj - 1)));
+                double dm = p.inv_az * ((FX3(s_Fuv, li + 1, lj) - FX3(s_Fuv, li, lj)) + (FYc(s_Fvv, li, lj) - FYc(s_Fvv, li, lj - 1)));
                 double pg = DIVDY(__dsub_rn(Pc, Ps));
-                double uhat = 0.5 * (0.5 * (AT(s_u, li, lj - 1) + AT(s_u, li + 1, lj - 1)) + 0.5 * (AT(s_u, li, lj) + AT(s_u, li + 1, lj)));
-                double lor = p.inv_az * ((AT(s_Lxy, li + 1, lj) - AT(s_Lxy, li, lj)) + (AT(s_Lyy, li, lj) - AT(s_Lyy, li, lj - 1)));
+                double uhat = avg4(RAW(s_u, li, lj - 1), RAW(s_u, li + 1, lj - 1), RAW(s_u, li, lj), RAW(s_u, li + 1, lj));
+                double lor = p.inv_az * ((FX3(s_Lxy, li + 1, lj) - FX3(s_Lxy, li, lj)) + (FYc(s_Lyy, li, lj) - FYc(s_Lyy, li, lj - 1)));
                 Gn1 = ((-dm - pg) - p.f * uhat) + lor;
             }
             {   // Gh (centred), GA
-                double dv = p.inv_az * ((p.dy * AT(s_u, li + 1, lj) - p.dy * AT(s_u, li, lj)) +
-                                        (p.dx * AT(s_v, li, lj + 1) - p.dx * AT(s_v, li, lj)));
+#if SWMHD_STRICT
+                double dv = p.inv_az * ((p.dy * RAW(s_u, li + 1, lj) - p.dy * RAW(s_u, li, lj)) +
+                                        (p.dx * RAW(s_v, li, lj + 1) - p.dx * RAW(s_v, li, lj)));
+#else
+                double dv = fma(RAW(s_u, li + 1, lj) - RAW(s_u, li, lj), p.rdx, (RAW(s_v, li, lj + 1) - RAW(s_v, li, lj)) * p.rdy);
+#endif
                 Gn2 = -dv;
-                double d = p.inv_az * ((AT(s_Tx, li + 1, lj) - AT(s_Tx, li, lj)) + (AT(s_Ty, li, lj + 1) - AT(s_Ty, li, lj)));
-                double cdiv = DIVDX(AT(s_uq, li + 1, lj) - AT(s_uq, li, lj)) + DIVDY(AT(s_vq, li, lj + 1) - AT(s_vq, li, lj));
-                Gn3 = -d + AT(s_A, li, lj) * cdiv;
+                double d = p.inv_az * ((FX3(s_Tx, li + 1, lj) - FX3(s_Tx, li, lj)) + (FY3(s_Ty, li, lj + 1) - FY3(s_Ty, li, lj)));
+                double cdiv = DIVDX(FX3(s_uq, li + 1, lj) - FX3(s_uq, li, lj)) + DIVDY(FY3(s_vq, li, lj + 1) - FY3(s_vq, li, lj));
+                Gn3 = -d + RAW(s_A, li, lj) * cdiv;
             }
         }
     }
 
     // ---- RK3 substep + stores ---------------------------------------------------------
     if (active) {
-        const size_t g = (size_t)(i + 2) + (size_t)P * (size_t)(j + 2);
         const double Gn[4] = {Gn0, Gn1, Gn2, Gn3};
-        const double Uc[4] = {AT(s_u, li, lj), AT(s_v, li, lj), AT(s_h, li, lj), AT(s_A, li, lj)};
+        const double Gm[4] = {Gm0, Gm1, Gm2, Gm3};
+        const double Uc[4] = {RAW(s_u, li, lj), RAW(s_v, li, lj), RAW(s_h, li, lj), RAW(s_A, li, lj)};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             if constexpr (STAGE == 0) {
-                p.G[k][g] = Gn[k];
+                p.G[k][gcell] = Gn[k];
             } else if constexpr (STAGE == 1) {
-                p.Un[k][g] = Uc[k] + p.dtgam * Gn[k];
-                p.G[k][g] = Gn[k];
+                p.Un[k][gcell] = Uc[k] + p.dtgam * Gn[k];
+                p.G[k][gcell] = Gn[k];
             } else {
-                double gm = p.G[k][g];
-                p.Un[k][g] = Uc[k] + p.dt * (p.gam * Gn[k] + p.zet * gm);
-                if constexpr (STAGE == 2) p.G[k][g] = Gn[k];
+                p.Un[k][gcell] = Uc[k] + p.dt * (p.gam * Gn[k] + p.zet * Gm[k]);
+                if constexpr (STAGE == 2) p.G[k][gcell] = Gn[k];
             }
+        }
+    }
+
+    // ---- fused diagnostics of the state at the start of the step -------------
+    if constexpr (DIAG) {
+        double ke = 0, me = 0, pe = 0, sh = 0, mu = 0, mA = 0, mh = -INFINITY, md = 0, nf = 0;
+        if (active) {
+            auto sq = [](double x) { return x * x; };
+            double hh = RAW(s_h, li, lj), aa = RAW(s_A, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj);
+            // KE bracket u^2 + ℑxyᶠᶜᵃ(v^2) at fcc(i) and fcc(i+1), averaged to the centre
+            auto keb = [&](int a) {
+                return sq(RAW(s_u, a, lj)) + avg4(sq(RAW(s_v, a - 1, lj)), sq(RAW(s_v, a, lj)), sq(RAW(s_v, a - 1, lj + 1)), sq(RAW(s_v, a, lj + 1)));
+            };
+            double wgt = (FORM == 0) ? 0.5 * hh : 0.5 * fdiv(1.0, hh);
+            ke = wgt * (0.5 * (keb(li) + keb(li + 1)));
+            // ME bracket Bx^2 + ℑxyᶜᶠᵃ(By^2) at cfc(j) and cfc(j+1)
+            auto SQBX = [&](int a, int b) { return s_sqBx[(b - 3) * YP + a - 3]; };
+            auto SQBY = [&](int a, int b) { return s_sqBy[(b - 2) * XP + a - 3]; };
+            auto meb = [&](int b) {
+                return SQBX(li, b) + avg4(SQBY(li, b - 1), SQBY(li + 1, b - 1), SQBY(li, b), SQBY(li + 1, b));
+            };
+            me = (0.5 * hh) * (0.5 * (meb(lj) + meb(lj + 1)));
+            double dh = hh - p.h_ref;
+            pe = (0.5 * p.g) * (dh * dh);
+            sh = hh;
+            mu = (FORM == 0) ? fabs(uu) : fabs(fdiv(uu, 0.5 * (RAW(s_h, li - 1, lj) + hh)));
+            mA = fabs(aa);
+            mh = -hh;
+            // div(hB) at ccc with hBx, hBy of sw_mhd_divergence_functions.jl:142-148
+            auto DyA = [&](int a, int b) { return DIVDY(RAW(s_A, a, b) - RAW(s_A, a, b - 1)); };
+            auto DxA = [&](int a, int b) { return DIVDX(RAW(s_A, a, b) - RAW(s_A, a - 1, b)); };
+            auto hBx = [&](int a, int b) { return -avg4(DyA(a - 1, b), DyA(a, b), DyA(a - 1, b + 1), DyA(a, b + 1)); };
+            auto hBy = [&](int a, int b) { return avg4(DxA(a, b - 1), DxA(a + 1, b - 1), DxA(a, b), DxA(a + 1, b)); };
+            md = fabs(DIVDX(hBx(li + 1, lj) - hBx(li, lj)) + DIVDY(hBy(li, lj + 1) - hBy(li, lj)));
+            if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) nf = 1.0;
+        }
+        __shared__ double red[NDIAG][NT / 32];
+        const int lane = tid & 31, wid = tid >> 5;
+        double r[NDIAG] = {warp_sum(ke), warp_sum(me), warp_sum(pe), warp_sum(sh), warp_max(mu),
+                           warp_max(mA), warp_max(mh), warp_max(md), warp_sum(nf)};
+        if (lane == 0)
+            for (int q = 0; q < NDIAG; q++) red[q][wid] = r[q];
+        __syncthreads();
+        if (tid < NDIAG) {
+            double acc = red[tid][0];
+            const bool is_max = (tid >= 4 && tid <= 7);
+            for (int w = 1; w < NT / 32; w++) acc = is_max ? fmax(acc, red[tid][w]) : acc + red[tid][w];
+            const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+            p.diag[blk * NDIAG + tid] = acc;          // slot 6 holds max(-h) = -min h
         }
     }
 }
 
-template <int FORM, int STAGE>
+template <int FORM, int STAGE, bool DIAG>
 cudaError_t launch_one(const KParams &p, cudaStream_t st) {
-    constexpr size_t bytes = (size_t)Smem<FORM>::NARR * SZ * sizeof(double);
+    constexpr size_t bytes = (size_t)SmemLayout<FORM, DIAG>::total * sizeof(double);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(substage_kernel<FORM, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t e = cudaFuncSetAttribute(substage_kernel<FORM, STAGE, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     dim3 grid((p.Nx + TX - 1) / TX, p.tile_rows);
-    substage_kernel<FORM, STAGE><<<grid, NT, bytes, st>>>(p);
+    substage_kernel<FORM, STAGE, DIAG><<<grid, NT, bytes, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -496,15 +692,17 @@ cudaError_t launch_one(const KParams &p, cudaStream_t st) {
 
 cudaError_t LAUNCH_NAME(const KParams &p, int form, int stage, cudaStream_t st) {
     if (p.tile_rows <= 0) return cudaSuccess;
+    const bool dg = (p.diag != nullptr);
+    if (dg && stage != 1) return cudaErrorInvalidValue;
     switch (form * 4 + stage) {
-        case 0: return launch_one<0, 0>(p, st);
-        case 1: return launch_one<0, 1>(p, st);
-        case 2: return launch_one<0, 2>(p, st);
-        case 3: return launch_one<0, 3>(p, st);
-        case 4: return launch_one<1, 0>(p, st);
-        case 5: return launch_one<1, 1>(p, st);
-        case 6: return launch_one<1, 2>(p, st);
-        case 7: return launch_one<1, 3>(p, st);
+        case 0: return launch_one<0, 0, false>(p, st);
+        case 1: return dg ? launch_one<0, 1, true>(p, st) : launch_one<0, 1, false>(p, st);
+        case 2: return launch_one<0, 2, false>(p, st);
+        case 3: return launch_one<0, 3, false>(p, st);
+        case 4: return launch_one<1, 0, false>(p, st);
+        case 5: return dg ? launch_one<1, 1, true>(p, st) : launch_one<1, 1, false>(p, st);
+        case 6: return launch_one<1, 2, false>(p, st);
+        case 7: return launch_one<1, 3, false>(p, st);
     }
     return cudaErrorInvalidValue;
 }

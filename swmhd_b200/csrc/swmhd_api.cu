@@ -22,7 +22,7 @@ struct swmhd_ctx {
     int cur;                    // U[cur] = current state
     double *d_partials, *d_diag; // diag partials; d_diag holds NDIAG doubles per slot
     int diag_slots;
-    int nblocks_diag;
+    int nblocks_diag, ntiles;
     cudaStream_t main, edge;
     bool own_streams;
     cudaEvent_t ev0, ev1, ev_edge, ev_main;
@@ -117,6 +117,8 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
         if ((e = cudaMemset(ctx->G[k], 0, bytes)) != cudaSuccess) return bail("cudaMemset", e);
     }
     ctx->nblocks_diag = diag_blocks(ctx->Nx, ctx->Ny);
+    ctx->ntiles = ((ctx->Nx + ctx->tx - 1) / ctx->tx) * ctx->ntr;
+    if (ctx->ntiles > ctx->nblocks_diag) ctx->nblocks_diag = ctx->ntiles;   // d_partials serves both diag paths
     ctx->diag_slots = 1024;
     if ((e = cudaMalloc(&ctx->d_partials, (size_t)ctx->nblocks_diag * NDIAG * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
     if ((e = cudaMalloc(&ctx->d_diag, (size_t)ctx->diag_slots * NDIAG * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
@@ -204,7 +206,7 @@ static KParams kparams(swmhd_ctx *ctx, double dt, int stage) {
     p.tile_row0 = 0; p.tile_rows = ctx->ntr;
     for (int k = 0; k < 4; k++) p.rows[k] = ctx->rows[k];
     p.dx = c.dx; p.dy = c.dy; p.rdx = 1.0 / c.dx; p.rdy = 1.0 / c.dy; p.inv_az = 1.0 / (c.dx * c.dy);
-    p.g = c.g; p.f = c.f; p.eps = c.weno_eps;
+    p.g = c.g; p.f = c.f; p.eps = c.weno_eps; p.h_ref = c.h_ref;
     p.dt = dt;
     p.gam = stage >= 1 ? RK_GAMMA[stage - 1] : 0.0;
     p.zet = stage >= 1 ? RK_ZETA[stage - 1] : 0.0;
@@ -242,9 +244,16 @@ extern "C" int swmhd_fill_halos(swmhd_ctx *ctx) {
 }
 
 // one substage on the main stream, no host synchronisation
-static int substage_async(swmhd_ctx *ctx, double dt, int stage) {
+static int substage_async(swmhd_ctx *ctx, double dt, int stage, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr, int diag_slot = -1) {
     KParams p = kparams(ctx, dt, stage);
+    if (diag_slot >= 0 && stage == 1) p.diag = ctx->d_partials;
+    if (e0) CK(cudaEventRecord(e0, ctx->main));
     CK(launch_substage(ctx, p, stage, ctx->main));
+    if (e1) CK(cudaEventRecord(e1, ctx->main));
+    if (diag_slot >= 0 && stage == 1) {
+        ctx->launches++;
+        CK(launch_diag_final(ctx->d_partials, ctx->ntiles, ctx->d_diag + (size_t)diag_slot * NDIAG, ctx->main));
+    }
     HaloParams h = halo_params(ctx, ctx->U[1 - ctx->cur], 3, ctx->Ny + 2, true);
     ctx->launches++;
     CK(launch_halo(h, ctx->main));
@@ -281,7 +290,7 @@ static void diag_fill(const swmhd_ctx *ctx, const double *r, swmhd_diag *o) {
     const double n = (double)c.Nx * (double)c.Ny, Lx = c.Nx * c.dx, Ly = c.Ny * c.dy;
     o->ke = r[0] / n * Lx * Ly; o->me = r[1] / n * Lx * Ly; o->pe = r[2] / n * Lx * Ly;
     o->total = o->ke + o->me + o->pe;
-    o->sum_h = r[3]; o->max_abs_u = r[4]; o->max_abs_A = r[5]; o->min_h = r[6]; o->max_abs_div_hB = r[7];
+    o->sum_h = r[3]; o->max_abs_u = r[4]; o->max_abs_A = r[5]; o->min_h = -r[6]; o->max_abs_div_hB = r[7];
     o->all_finite = (r[8] == 0.0) ? 1 : 0; o->reserved = 0;
 }
 
@@ -309,8 +318,8 @@ static int step_impl(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags) {
         int chunk = nsteps - done;
         if (diags && chunk > ctx->diag_slots) chunk = ctx->diag_slots;
         for (int n = 0; n < chunk; n++) {
-            if (diags) { int rc = diag_async(ctx, n); if (rc) return rc; }
-            for (int s = 1; s <= 3; s++) { int rc = substage_async(ctx, dt, s); if (rc) return rc; }
+            // diagnostics of the state at the start of the step: fused into the stage-1 kernel
+            for (int s = 1; s <= 3; s++) { int rc = substage_async(ctx, dt, s, nullptr, nullptr, diags ? n : -1); if (rc) return rc; }
         }
         if (diags) {
             host.resize((size_t)chunk * NDIAG);
@@ -332,6 +341,35 @@ extern "C" int swmhd_step(swmhd_ctx *ctx, double dt, int nsteps) { return step_i
 extern "C" int swmhd_step_diag(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags) {
     if (!diags) return ctx ? fail(ctx, SWMHD_ERR_ARG, "diags is null") : SWMHD_ERR_ARG;
     return step_impl(ctx, dt, nsteps, diags);
+}
+
+// nsteps RK3 steps with a CUDA-event pair around every substage-kernel launch (on the
+// launching stream); out_ms[s] = mean device duration of the stage-(s+1) kernel.
+extern "C" int swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) {
+    if (!ctx || !out_ms) return SWMHD_ERR_ARG;
+    if (nsteps < 1 || nsteps > 512) return fail(ctx, SWMHD_ERR_ARG, "nsteps must be in 1..512");
+    if (ctx->cfg.world != 1) return fail(ctx, SWMHD_ERR_STATE, "single-slab only");
+    CK(cudaSetDevice(ctx->cfg.device));
+    std::vector<cudaEvent_t> ev((size_t)nsteps * 6);
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    int rc = SWMHD_OK;
+    for (int n = 0; n < nsteps && rc == SWMHD_OK; n++)
+        for (int s = 1; s <= 3 && rc == SWMHD_OK; s++)
+            rc = substage_async(ctx, dt, s, ev[(size_t)n * 6 + 2 * (s - 1)], ev[(size_t)n * 6 + 2 * (s - 1) + 1]);
+    if (rc == SWMHD_OK) {
+        CK(cudaStreamSynchronize(ctx->main));
+        for (int s = 0; s < 3; s++) {
+            double acc = 0;
+            for (int n = 0; n < nsteps; n++) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, ev[(size_t)n * 6 + 2 * s], ev[(size_t)n * 6 + 2 * s + 1]));
+                acc += ms;
+            }
+            out_ms[s] = acc / nsteps;
+        }
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 extern "C" int swmhd_tendencies(swmhd_ctx *ctx, double *const G_host[4], size_t n_each) {

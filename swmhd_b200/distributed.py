@@ -1,0 +1,192 @@
+"""y-slab domain decomposition: one process per GPU, halo rows exchanged with
+`torch.distributed` point-to-point ops (NCCL over NVLink on GPUs, gloo in CPU tests).
+
+The reference is single-process; the decomposition is the one its layout
+suggests: rank p owns global rows [j0+1, j0+ny] plus 3 halo rows on each side, stored
+like an (Nx, ny) Field, so each halo message is a contiguous block of 3*(Nx+6) doubles
+per field and needs no packing.  Per substage:
+
+    edges    (high-priority stream)  rows within one tile of the slab edges, x-wrapped
+    exchange (NCCL stream)           send my edge rows, receive the neighbours' into my halos
+    interior (main stream)           everything else, concurrently with the exchange
+    finish                           join, swap buffers, tick the clock
+
+There is no data-path collective beyond this neighbour exchange; diagnostics are
+combined with one small all_reduce.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import abi
+
+# exchange_rows(which): see include/swmhd.h
+SOUTH_SEND, NORTH_SEND, SOUTH_HALO, NORTH_HALO = 0, 1, 2, 3
+CURRENT = 4  # add to `which` to address the current state instead of the one being written
+
+
+def split_rows(Ny: int, world: int):
+    """Contiguous row ranges [(j0, ny)] of the `world` slabs (first ranks take the remainder)."""
+    base, rem = divmod(Ny, world)
+    out, j0 = [], 0
+    for r in range(world):
+        ny = base + (1 if r < rem else 0)
+        out.append((j0, ny))
+        j0 += ny
+    return out
+
+
+def neighbours(rank: int, world: int, periodic_y: bool):
+    """(south, north) ranks or None at a wall."""
+    if world == 1:
+        return (rank, rank) if periodic_y else (None, None)
+    s = rank - 1 if rank > 0 else (world - 1 if periodic_y else None)
+    n = rank + 1 if rank < world - 1 else (0 if periodic_y else None)
+    return s, n
+
+
+def slab_config(cfg: abi.Config, rank: int, world: int, device: int = 0) -> abi.Config:
+    c = abi.Config.from_buffer_copy(cfg)
+    j0, ny = split_rows(cfg.Ny, world)[rank]
+    c.slab_j0, c.slab_ny, c.rank, c.world, c.device = j0, ny, rank, world, device
+    return c
+
+
+def slab_of_global(parent_global: np.ndarray, j0: int, ny: int, extra_rows: int = 0) -> np.ndarray:
+    """Rows of a global parent array that form the slab's parent array (3 halo rows each side)."""
+    return np.ascontiguousarray(parent_global[j0:j0 + ny + 6 + extra_rows])
+
+
+class _CudaRows:
+    """`__cuda_array_interface__` view of rows inside a libswmhd_cuda buffer."""
+
+    def __init__(self, ptr, nrows, width):
+        self.__cuda_array_interface__ = {
+            "shape": (nrows, width), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+def exchange_ops(rows_of, rank, world, periodic_y, tag_base=0):
+    """Build the P2P op list of one halo exchange.
+
+    rows_of(field, which) -> tensor of the 3 rows to send (which = SOUTH_SEND/NORTH_SEND) or to
+    receive into (SOUTH_HALO/NORTH_HALO).  My south edge rows go to the south neighbour's north
+    halo and vice versa.
+    """
+    s, n = neighbours(rank, world, periodic_y)
+    ops = []
+    for f in range(4):
+        if n is not None:
+            ops.append(dist.P2POp(dist.isend, rows_of(f, NORTH_SEND), n, tag=tag_base + 2 * f))
+        if s is not None:
+            ops.append(dist.P2POp(dist.irecv, rows_of(f, SOUTH_HALO), s, tag=tag_base + 2 * f))
+        if s is not None:
+            ops.append(dist.P2POp(dist.isend, rows_of(f, SOUTH_SEND), s, tag=tag_base + 2 * f + 1))
+        if n is not None:
+            ops.append(dist.P2POp(dist.irecv, rows_of(f, NORTH_HALO), n, tag=tag_base + 2 * f + 1))
+    return ops
+
+
+def self_exchange(rows_of):
+    """world == 1 with a slab-style context: periodic wrap by local copies."""
+    for f in range(4):
+        rows_of(f, SOUTH_HALO).copy_(rows_of(f, NORTH_SEND))
+        rows_of(f, NORTH_HALO).copy_(rows_of(f, SOUTH_SEND))
+
+
+@dataclass
+class SlabTimings:
+    ms: float = 0.0
+
+
+class SlabModel:
+    """One y-slab of the global grid on this process's GPU."""
+
+    def __init__(self, cfg_global: abi.Config, rank=None, world=None, device=None):
+        from .context import Context
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.device = torch.cuda.current_device() if device is None else device
+        self.cfg = slab_config(cfg_global, self.rank, self.world, self.device)
+        self.periodic_y = cfg_global.topo_y == abi.PERIODIC
+        self.ctx = Context(self.cfg)
+        self.main = torch.cuda.Stream(device=self.device)
+        self.edge = torch.cuda.Stream(device=self.device, priority=-1)
+        self.ctx.set_streams(self.main.cuda_stream, self.edge.cuda_stream)
+        self._views = {}
+
+    # -- row views --------------------------------------------------------------------------
+    def _rows(self, field, which):
+        ptr, n, w = self.ctx.exchange_rows(field, which)
+        t = self._views.get(ptr)
+        if t is None:
+            t = torch.as_tensor(_CudaRows(ptr, n, w), device=f"cuda:{self.device}")
+            self._views[ptr] = t
+        return t
+
+    def _exchange(self, current: bool, stream):
+        off = CURRENT if current else 0
+        rows_of = lambda f, which: self._rows(f, which + off)
+        if self.world == 1:
+            return []   # a single slab owns its own periodic wrap (done by the halo kernel)
+        ops = exchange_ops(rows_of, self.rank, self.world, self.periodic_y)
+        if not ops:
+            return []
+        with torch.cuda.stream(stream):
+            return dist.batch_isend_irecv(ops)
+
+    # -- state ------------------------------------------------------------------------------
+    def set_state(self, U_slab):
+        self.ctx.set_state(U_slab)
+
+    def get_state(self):
+        return self.ctx.get_state()
+
+    def fill_halos(self):
+        """update_state! after set!: x wrap / walls locally, y halos from the neighbours."""
+        self.ctx.fill_halos()
+        works = self._exchange(current=True, stream=self.main)
+        with torch.cuda.stream(self.main):
+            for w in works:
+                w.wait()
+        self.main.synchronize()
+
+    # -- stepping ---------------------------------------------------------------------------
+    def substage(self, dt, stage):
+        self.ctx.substage_edges(dt, stage)
+        works = self._exchange(current=False, stream=self.edge)
+        self.ctx.substage_interior(dt, stage)
+        with torch.cuda.stream(self.main):
+            for w in works:
+                w.wait()
+        self.ctx.substage_finish(stage)
+
+    def step(self, dt, nsteps=1):
+        for _ in range(nsteps):
+            for stage in (1, 2, 3):
+                self.substage(dt, stage)
+
+    def synchronize(self):
+        self.ctx.sync()
+
+    def diagnostics(self) -> dict:
+        """Slab partials are already scaled by the global normalisation: sums add, extrema combine."""
+        d = self.ctx.diagnostics(check_finite=False)
+        if self.world == 1:
+            return d
+        dev = f"cuda:{self.device}"
+        sums = torch.tensor([d["ke"], d["me"], d["pe"], d["sum_h"], float(1 - d["all_finite"])], dtype=torch.float64, device=dev)
+        maxs = torch.tensor([d["max_abs_u"], d["max_abs_A"], d["max_abs_div_hB"], -d["min_h"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
+        s, m = sums.tolist(), maxs.tolist()
+        return dict(ke=s[0], me=s[1], pe=s[2], total=s[0] + s[1] + s[2], sum_h=s[3], all_finite=int(s[4] == 0),
+                    max_abs_u=m[0], max_abs_A=m[1], max_abs_div_hB=m[2], min_h=-m[3])
+
+    def close(self):
+        self._views.clear()
+        self.ctx.close()

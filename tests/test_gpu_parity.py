@@ -102,3 +102,35 @@ def test_fast_1000_steps(kind, form_tol):
     for k in range(4):
         err = rel_l2(g, Ug[k], U[k], k)
         assert err <= form_tol, f"field {k}: rel L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("kind", ["J", "D"])
+@pytest.mark.parametrize("arith", [abi.ARITH_FAST, abi.ARITH_STRICT])
+def test_fused_step_diagnostics(kind, arith):
+    """swmhd_step_diag: the diagnostics fused into the stage-1 kernel equal the oracle's
+    diagnostics of the state at the start of every step, and do not perturb the step."""
+    g, cfg, U = make_case(kind, 100, Ny=72, arith=arith, perturb=9)
+    ctx = Context(cfg)
+    ctx.set_state(U)
+    ctx.fill_halos()
+    dg = ctx.step_diag(0.004, 3)
+    Ug = ctx.get_state()
+    ctx.close()
+    ctx2 = Context(cfg)
+    ctx2.set_state(U)
+    ctx2.fill_halos()
+    ctx2.step(0.004, 3)
+    Up = ctx2.get_state()
+    ctx2.close()
+    for k in range(4):
+        assert np.array_equal(Ug[k], Up[k])
+    O.fill_halos(cfg, U)
+    for n in range(3):
+        do = O.diagnostics(cfg, U)
+        for key in ("ke", "me", "pe", "total", "sum_h"):
+            assert abs(dg[n][key] - do[key]) <= 2e-13 * max(1.0, abs(do[key])), (n, key, dg[n][key], do[key])
+        for key in ("max_abs_A", "min_h"):
+            assert dg[n][key] == do[key], (n, key)
+        assert abs(dg[n]["max_abs_u"] - do["max_abs_u"]) <= 1e-15 * max(1.0, do["max_abs_u"])
+        assert abs(dg[n]["max_abs_div_hB"] - do["max_abs_div_hB"]) < 1e-13
+        O.step(cfg, U, 0.004, 1)
