@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace swmhd {
@@ -23,6 +24,8 @@ struct KParams {
     const double *Uo[4]; // state at the start of the substage (halos valid)
     double *Un[4];       // state after the substage (interior written)
     double *G[4];        // G^- on entry (stages 2,3), G^n on exit (stages 1,2)
+    int use_tma;         // 1: tm[] are valid tensor maps of Uo[] (TMA tile loads)
+    alignas(64) CUtensorMap tm[4];
     double *diag;        // per-CTA diagnostic partials [tiles][NDIAG] (stage-1 DIAG variant), or nullptr
 };
 

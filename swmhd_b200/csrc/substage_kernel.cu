@@ -23,6 +23,7 @@
 //       Lorentz force, U += dt(gamma G^n + zeta G^-), store U_new and G^n.
 // HBM traffic per cell and substage: 4-8 reads + 4-8 writes of doubles (algorithmic).
 #include "kparams.h"
+#include <cstdlib>
 
 #ifndef SWMHD_STRICT
 #error "compile with -DSWMHD_STRICT=0|1"
@@ -37,8 +38,13 @@ namespace {
 #define LAUNCH_NAME launch_substage_fast
 #endif
 
+#ifndef SWMHD_MINB
+#define SWMHD_MINB 3
+#endif
 constexpr int TX = 32, TY = 8, NT = 256;
-constexpr int W = TX + 6, HT = TY + 6, SZ = W * HT;        // raw tiles: [HT][W]
+constexpr int W = TX + 6, HT = TY + 6, SZ = W * HT;        // raw tiles: [HT][W] (dense TMA box)
+constexpr int SZP = (SZ * 8 + 127) / 128 * 16;             // raw tile padded to a multiple of 128 B (TMA dst alignment)
+constexpr unsigned TILE_TX_BYTES = 4u * SZ * 8u;           // bytes one tile load brings in (4 fields)
 
 // compact derived / flux arrays: (pitch, rows)
 constexpr int ZP = TX + 5, ZR = TY + 5;     // ffc points a in [1,TX+5], b in [1,TY+5]
@@ -194,9 +200,12 @@ __device__ __forceinline__ double upwind_weno(const double *ctr, int st, double 
     const int s = pos ? st : -st;
     return vel * weno5(q[0], q[s], q[2 * s], q[3 * s], q[4 * s], eps);
 }
+// Bounded-y wall buffer variant: centred 2nd order instead of WENO5 (selected, not branched, so that
+// several reconstructions of one thread stay in one basic block and their FP64 chains interleave)
 __device__ __forceinline__ double upwind_weno_buf(const double *ctr, int st, double vel, double eps, bool buf) {
-    if (buf) return vel * sym2(ctr[-st], ctr[0]);
-    return upwind_weno(ctr, st, vel, eps);
+    const double w = upwind_weno(ctr, st, vel, eps);
+    const double c2 = vel * sym2(ctr[-st], ctr[0]);
+    return buf ? c2 : w;
 }
 __device__ __forceinline__ double upwind_sel(double vel, double L, double R) {
     return vel * (vel > 0.0 ? L : R);
@@ -213,11 +222,36 @@ __device__ __forceinline__ double warp_max(double x) {
     return x;
 }
 
+// ---- TMA + mbarrier (sm_90+/sm_100a): cp.async.bulk.tensor into shared memory ------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 constexpr int NDG_ = YP * YR + XP * (TY + 2);   // diag scratch: sqBx (YP*YR) + sqBy (XP*(TY+2))
 template <int FORM, bool DIAG> struct SmemLayout;
 template <bool DIAG> struct SmemLayout<0, DIAG> {
-    static constexpr int o_z = 4 * SZ, o_ut = o_z + ZP * ZR, o_vt = o_ut + ZP * ZR;
+    static constexpr int o_z = 0, o_ut = o_z + ZP * ZR, o_vt = o_ut + ZP * ZR;
     static constexpr int o_K = o_vt + ZP * ZR, o_Bx = o_K + CP * CR, o_By = o_Bx + CP * CR;
     static constexpr int o_Fxh = o_By + CP * CR, o_FxA = o_Fxh + XP * XR;
     static constexpr int o_Fyh = o_FxA + XP * XR, o_FyA = o_Fyh + YP * YR;
@@ -225,7 +259,7 @@ template <bool DIAG> struct SmemLayout<0, DIAG> {
     static constexpr int total = o_dg + (DIAG ? NDG_ : 0);
 };
 template <bool DIAG> struct SmemLayout<1, DIAG> {
-    static constexpr int o_hBx = 4 * SZ, o_hBy = o_hBx + BP * BR, o_Bx = o_hBy + BP * BR, o_By = o_Bx + BP * BR;
+    static constexpr int o_hBx = 0, o_hBy = o_hBx + BP * BR, o_Bx = o_hBy + BP * BR, o_By = o_Bx + BP * BR;
     static constexpr int o_hx = o_By + BP * BR, o_hy = o_hx + BP * BR, o_hff = o_hy + BP * BR;
     static constexpr int o_Fuu = o_hff + XP * YR, o_Lxx = o_Fuu + XP * XR, o_Fuv = o_Lxx + XP * XR, o_Lxy = o_Fuv + XP * XR;
     static constexpr int o_Tx = o_Lxy + XP * XR, o_uq = o_Tx + XP * XR;
@@ -236,47 +270,92 @@ template <bool DIAG> struct SmemLayout<1, DIAG> {
 };
 
 // STAGE 1,2,3; 0 = tendencies only (G written, U untouched).  DIAG only with STAGE 1.
-template <int FORM, int STAGE, bool DIAG>
-__global__ void __launch_bounds__(NT, 3) substage_kernel(const KParams p) {
-    extern __shared__ double smem[];
+// Persistent: gridDim.x CTAs loop over the tiles of the launch (x fastest, so concurrently
+// resident CTAs share their halo columns/rows through L2).  NSTG = 2 double-buffers the raw
+// tile: the TMA load of tile n+1 overlaps the arithmetic of tile n.  TMA = false is the
+// plain-load path (odd Nx: the row pitch is not a multiple of 16 B).
+template <int FORM, int STAGE, bool DIAG, bool TMA, int NSTG>
+__global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ unsigned char smem_bytes[];
     using L = SmemLayout<FORM, DIAG>;
-    double *s_u = smem, *s_v = smem + SZ, *s_h = smem + 2 * SZ, *s_A = smem + 3 * SZ;
+    double *const raw0 = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(smem_bytes) + 127) & ~uintptr_t(127));
+    double *const smem = raw0 + NSTG * 4 * SZP;             // derived / flux arrays
+    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + L::total);
     const int tid = threadIdx.x;
-    const int i0 = blockIdx.x * TX + 1;                     // logical (1-based) first cell
-    const int j0 = (blockIdx.y + p.tile_row0) * TY + 1;
     const int Nx = p.Nx, Ny = p.Ny, P = p.P;
     const double eps = p.eps;
+    const int tiles_x = (Nx + TX - 1) / TX;
+    const int ntiles = tiles_x * p.tile_rows;
 
-    // own cell of this thread
+    if constexpr (TMA) {
+        if (tid == 0) {
+            for (int s = 0; s < NSTG; s++) mbar_init(&mbar[s], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
+    auto issue_load = [&](int tile, int stage) {            // one elected thread
+        const int c0 = (tile % tiles_x) * TX;                // parent column of local a = 0
+        const int c1 = (p.tile_row0 + tile / tiles_x) * TY;  // parent row of local b = 0
+        double *dst = raw0 + stage * 4 * SZP;
+        mbar_expect_tx(&mbar[stage], TILE_TX_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; k++) tma_load_2d(dst + k * SZP, &p.tm[k], c0, c1, &mbar[stage]);
+    };
+    if constexpr (TMA && NSTG == 2) {
+        if (tid == 0 && (int)blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
+    }
+
+    // own cell of this thread (tile-local)
     const int tx = tid % TX, ty = tid / TX;
     const int li = tx + 3, lj = ty + 3;
+    double *s_sqBx = smem + L::o_dg, *s_sqBy = s_sqBx + YP * YR;   // DIAG only
+    (void)s_sqBx; (void)s_sqBy;
+
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int stg = (NSTG == 2) ? (it & 1) : 0;
+    double *s_u = raw0 + stg * 4 * SZP, *s_v = s_u + SZP, *s_h = s_u + 2 * SZP, *s_A = s_u + 3 * SZP;
+    const int i0 = (tile % tiles_x) * TX + 1;               // logical (1-based) first cell
+    const int j0 = (p.tile_row0 + tile / tiles_x) * TY + 1;
     const int i = i0 + tx, j = j0 + ty;
     const bool active = (i <= Nx) && (j <= Ny);
     const int gj = p.gj0 + j;                               // global row (wall logic)
     const size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(j + 2);
 
+    // ---- P0: stage the four fields with a 3-cell halo -------------------------------
+    if constexpr (TMA) {
+        if (tid == 0) {
+            if constexpr (NSTG == 2) {
+                const int nxt = tile + gridDim.x;            // prefetch: overlaps this tile's arithmetic
+                if (nxt < ntiles) issue_load(nxt, stg ^ 1);
+            } else {
+                issue_load(tile, 0);
+            }
+        }
+    }
     // G^- of the own cell: issue the loads now, consume them after the tendencies
     double Gm0 = 0.0, Gm1 = 0.0, Gm2 = 0.0, Gm3 = 0.0;
     if constexpr (STAGE >= 2) {
         if (active) { Gm0 = p.G[0][gcell]; Gm1 = p.G[1][gcell]; Gm2 = p.G[2][gcell]; Gm3 = p.G[3][gcell]; }
     }
-
-    // ---- P0: stage the four fields with a 3-cell halo -------------------------------
-    for (int t = tid; t < SZ; t += NT) {
-        int a = t % W, b = t / W;
-        int pi = i0 - 1 + a, pj = j0 - 1 + b;               // parent (0-based) column / row
-        bool okx = pi < P;
-        size_t g = (size_t)pi + (size_t)P * (size_t)pj;
-        s_u[t] = (okx && pj < p.rows[0]) ? p.Uo[0][g] : 0.0;
-        s_v[t] = (okx && pj < p.rows[1]) ? p.Uo[1][g] : 0.0;
-        s_h[t] = (okx && pj < p.rows[2]) ? p.Uo[2][g] : 1.0;
-        s_A[t] = (okx && pj < p.rows[3]) ? p.Uo[3][g] : 0.0;
+    if constexpr (TMA) {
+        mbar_wait(&mbar[stg], (NSTG == 2) ? ((it >> 1) & 1) : (it & 1));
+    } else {
+        for (int t = tid; t < SZ; t += NT) {
+            int a = t % W, b = t / W;
+            int pi = i0 - 1 + a, pj = j0 - 1 + b;           // parent (0-based) column / row
+            bool okx = pi < P;
+            size_t g = (size_t)pi + (size_t)P * (size_t)pj;
+            s_u[t] = (okx && pj < p.rows[0]) ? p.Uo[0][g] : 0.0;
+            s_v[t] = (okx && pj < p.rows[1]) ? p.Uo[1][g] : 0.0;
+            s_h[t] = (okx && pj < p.rows[2]) ? p.Uo[2][g] : 1.0;
+            s_A[t] = (okx && pj < p.rows[3]) ? p.Uo[3][g] : 0.0;
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     double Gn0 = 0.0, Gn1 = 0.0, Gn2 = 0.0, Gn3 = 0.0;
-    double *s_sqBx = smem + L::o_dg, *s_sqBy = s_sqBx + YP * YR;   // DIAG only
-    (void)s_sqBx; (void)s_sqBy;
 
     if constexpr (FORM == 0) {
         // ================= VectorInvariant + Jacobian Lorentz ======================
@@ -288,23 +367,11 @@ __global__ void __launch_bounds__(NT, 3) substage_kernel(const KParams p) {
 #define FX(arr, a, b) arr[((b) - 3) * XP + (a) - 3]
 #define FY(arr, a, b) arr[((b) - 3) * YP + (a) - 3]
 
-        // ---- P1: one task list (heavy face fluxes first, light derived fields after) -----
+        // ---- A: light derived fields (zeta, velocity-stencil averages, K, Bx, By [, diag B^2]) ----
         constexpr int NXF = XP * XR, NYF = YP * YR, NZ = ZP * ZR, NC = CP * CR;
         constexpr int NDG = DIAG ? NDG_ : 0;
-        for (int t = tid; t < NXF + NYF + NZ + NC + NDG; t += NT) {
-            if (t < NXF) {                                          // x-face (fcc): mass and tracer flux
-                int a = 3 + t % XP, b = 3 + t / XP;
-                double vel = RAW(s_u, a, b);
-                FX(s_Fxh, a, b) = p.dy * upwind_weno(&RAW(s_h, a, b), 1, vel, eps);
-                FX(s_FxA, a, b) = p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps);
-            } else if (t < NXF + NYF) {                             // y-face (cfc)
-                int q = t - NXF;
-                int a = 3 + q % YP, b = 3 + q / YP;
-                double vel = RAW(s_v, a, b);
-                bool buf = ybuf(p.by, p.gj0 + j0 + (b - 3), 3, p.NyG);
-                FY(s_Fyh, a, b) = p.dx * upwind_weno_buf(&RAW(s_h, a, b), W, vel, eps, buf);
-                FY(s_FyA, a, b) = p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, buf);
-            } else if (t < NXF + NYF + NZ) {                        // zeta, ℑy u, ℑx v at ffc
+        for (int t = tid + NXF + NYF; t < NXF + NYF + NZ + NC + NDG; t += NT) {
+            if (t < NXF + NYF + NZ) {                               // zeta, ℑy u, ℑx v at ffc
                 int q = t - NXF - NYF;
                 int a = 1 + q % ZP, b = 1 + q / ZP;
                 double vc = RAW(s_v, a, b), vw = RAW(s_v, a - 1, b), uc = RAW(s_u, a, b), us = RAW(s_u, a, b - 1);
@@ -349,20 +416,54 @@ __global__ void __launch_bounds__(NT, 3) substage_kernel(const KParams p) {
         }
         __syncthreads();
 
+        // ---- B: all WENO5 work.  Every thread evaluates, in one straight-line block, the six
+        // independent reconstructions of its own cell (vorticity along y and x with VelocityStencil
+        // smoothness; h and A at the west and the south face), so their FP64 dependency chains
+        // interleave.  Warps 0/1 add the tile's north row / east column of faces.
+        double adv_u, adv_v, vhat, uhat;
+        {
+            vhat = avg4(RAW(s_v, li - 1, lj), RAW(s_v, li, lj), RAW(s_v, li - 1, lj + 1), RAW(s_v, li, lj + 1));
+            uhat = avg4(RAW(s_u, li, lj - 1), RAW(s_u, li + 1, lj - 1), RAW(s_u, li, lj), RAW(s_u, li + 1, lj));
+            const bool posv = vhat > 0.0, posu = uhat > 0.0;
+            const int lfy = lj + 1, lfx = li + 1;                   // zeta to the centre j (along y) / i (along x)
+            const int offy = ((posv ? lfy - 3 : lfy + 2) - 1) * ZP + li - 1;
+            const int offx = (lj - 1) * ZP + (posu ? lfx - 3 : lfx + 2) - 1;
+            const double zy = weno5_vs(s_z + offy, s_ut + offy, s_vt + offy, posv ? ZP : -ZP, eps);
+            const double zx = weno5_vs(s_z + offx, s_ut + offx, s_vt + offx, posu ? 1 : -1, eps);
+            const double z2 = sym2(Zf(s_z, li, lfy - 1), Zf(s_z, li, lfy));
+            adv_u = vhat * (ybuf(p.by, gj + 1, 3, p.NyG + 1) ? z2 : zy);
+            adv_v = uhat * zx;
+            // west (fcc) and south (cfc) faces of the own cell: mass and tracer fluxes
+            const double uw = RAW(s_u, li, lj), vs = RAW(s_v, li, lj);
+            const bool buf = ybuf(p.by, gj, 3, p.NyG);
+            const double fxh = upwind_weno(&RAW(s_h, li, lj), 1, uw, eps);
+            const double fxA = upwind_weno(&RAW(s_A, li, lj), 1, uw, eps);
+            const double fyh = upwind_weno_buf(&RAW(s_h, li, lj), W, vs, eps, buf);
+            const double fyA = upwind_weno_buf(&RAW(s_A, li, lj), W, vs, eps, buf);
+            FX(s_Fxh, li, lj) = p.dy * fxh; FX(s_FxA, li, lj) = p.dy * fxA;
+            FY(s_Fyh, li, lj) = p.dx * fyh; FY(s_FyA, li, lj) = p.dx * fyA;
+        }
+        if (tid < 32) {                                             // north row of y-faces, b = TY+3
+            const int a = 3 + tid, b = TY + 3;
+            const double vs = RAW(s_v, a, b);
+            const bool buf = ybuf(p.by, p.gj0 + j0 + TY, 3, p.NyG);
+            const double fyh = upwind_weno_buf(&RAW(s_h, a, b), W, vs, eps, buf);
+            const double fyA = upwind_weno_buf(&RAW(s_A, a, b), W, vs, eps, buf);
+            FY(s_Fyh, a, b) = p.dx * fyh; FY(s_FyA, a, b) = p.dx * fyA;
+        } else if (tid < 32 + TY) {                                 // east column of x-faces, a = TX+3
+            const int a = TX + 3, b = 3 + (tid - 32);
+            const double uw = RAW(s_u, a, b);
+            const double fxh = upwind_weno(&RAW(s_h, a, b), 1, uw, eps);
+            const double fxA = upwind_weno(&RAW(s_A, a, b), 1, uw, eps);
+            FX(s_Fxh, a, b) = p.dy * fxh; FX(s_FxA, a, b) = p.dy * fxA;
+        }
+        __syncthreads();
+
         // ---- P2: tendencies of the own cell -------------------------------------------
         if (active) {
             // Gu at fcc
             {
-                double vhat = avg4(RAW(s_v, li - 1, lj), RAW(s_v, li, lj), RAW(s_v, li - 1, lj + 1), RAW(s_v, li, lj + 1));
-                const int lf = lj + 1;                              // zeta along y to centre j
-                double adv;
-                if (ybuf(p.by, gj + 1, 3, p.NyG + 1)) {
-                    adv = vhat * sym2(Zf(s_z, li, lf - 1), Zf(s_z, li, lf));
-                } else {
-                    const bool pos = vhat > 0.0;
-                    const int off = ((pos ? lf - 3 : lf + 2) - 1) * ZP + li - 1;
-                    adv = vhat * weno5_vs(s_z + off, s_ut + off, s_vt + off, pos ? ZP : -ZP, eps);
-                }
+                const double adv = adv_u;
                 double dK = DIVDX(Cc(s_K, li, lj) - Cc(s_K, li - 1, lj));
                 double pg = p.g * DIVDX(RAW(s_h, li, lj) - RAW(s_h, li - 1, lj));
                 // lorentz_force_func_x — sw_mhd_jacobian_functions.jl:10-13,20-22
@@ -386,11 +487,7 @@ __global__ void __launch_bounds__(NT, 3) substage_kernel(const KParams p) {
             }
             // Gv at cfc (wall rows of a Bounded-y grid keep v = 0)
             if (!(p.by && gj < 2)) {
-                double uhat = avg4(RAW(s_u, li, lj - 1), RAW(s_u, li + 1, lj - 1), RAW(s_u, li, lj), RAW(s_u, li + 1, lj));
-                const int lf = li + 1;                              // zeta along x to centre i
-                const bool pos = uhat > 0.0;
-                const int off = (lj - 1) * ZP + (pos ? lf - 3 : lf + 2) - 1;
-                double adv = uhat * weno5_vs(s_z + off, s_ut + off, s_vt + off, pos ? 1 : -1, eps);
+                const double adv = adv_v;
                 double dK = DIVDY(Cc(s_K, li, lj) - Cc(s_K, li, lj - 1));
                 double pg = p.g * DIVDY(RAW(s_h, li, lj) - RAW(s_h, li, lj - 1));
                 // lorentz_force_func_y — sw_mhd_jacobian_functions.jl:15-18,24-26
@@ -470,90 +567,93 @@ __global__ void __launch_bounds__(NT, 3) substage_kernel(const KParams p) {
         constexpr int NXF = XP * XR, NYF = YP * YR;
         constexpr int NDG = DIAG ? NDG_ : 0;
         const int NyG = p.NyG, by = p.by;
-        for (int t = tid; t < 3 * NXF + 3 * NYF + NDG; t += NT) {
-            if (t < NXF) {                      // ccc (i0-1..i0+TX-1, j): F_uu and Lxx
-                int a = 2 + t % XP, b = 3 + t / XP;
-                double ut = sym4(RAW(s_u, a - 1, b), RAW(s_u, a, b), RAW(s_u, a + 1, b), RAW(s_u, a + 2, b));
-                FXc(s_Fuu, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_u, a + 1, b), 1, ut, eps), RAW(s_h, a, b));
-                // advective_lorentz_flux_hBx_bx :38-60 (x periodic: final else branch)
-                double ul = 0.5 * (Bf(s_hBx, a, b) + Bf(s_hBx, a + 1, b));
-                double Lq = third(Bf(s_Bx, a + 1, b), Bf(s_Bx, a, b), Bf(s_Bx, a - 1, b));
-                double Rq = thirdR(Bf(s_Bx, a + 2, b), Bf(s_Bx, a + 1, b), Bf(s_Bx, a, b));
-                FXc(s_Lxx, a, b) = p.dy * upwind_sel(ul, Lq, Rq);
-            } else if (t < 2 * NXF) {           // ffc (i0..i0+TX, j): F_uv and Lxy
-                int q = t - NXF;
-                int a = 3 + q % XP, b = 3 + q / XP;
-                int gjf = p.gj0 + j0 + (b - 3);
-                double ut = ybuf(by, gjf, 2, NyG) ? sym2(RAW(s_u, a, b - 1), RAW(s_u, a, b))
-                                                  : sym4(RAW(s_u, a, b - 2), RAW(s_u, a, b - 1), RAW(s_u, a, b), RAW(s_u, a, b + 1));
-                FX3(s_Fuv, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_v, a, b), 1, ut, eps), HF(a, b));
-                // advective_lorentz_flux_hBx_by :86-108
-                double ul = 0.5 * (Bf(s_hBx, a, b - 1) + Bf(s_hBx, a, b));
-                double Lq = third(Bf(s_By, a, b), Bf(s_By, a - 1, b), Bf(s_By, a - 2, b));
-                double Rq = thirdR(Bf(s_By, a + 1, b), Bf(s_By, a, b), Bf(s_By, a - 1, b));
-                FX3(s_Lxy, a, b) = p.dy * upwind_sel(ul, Lq, Rq);
-            } else if (t < 3 * NXF) {           // fcc (i0..i0+TX, j): tracer transport flux, uh/ℑx h
-                int q = t - 2 * NXF;
-                int a = 3 + q % XP, b = 3 + q / XP;
-                double vel = RAW(s_u, a, b), hx = Bf(s_hx, a, b);
+        // Six flux families, one WENO5 each.  Every thread evaluates the six fluxes anchored at its own
+        // cell in one straight-line block (independent FP64 chains interleave); warps 0/1 add the
+        // tile's north row / east column.
+        auto flux_uu = [&](int a, int b) {      // ccc: F_uu and Lxx (advective_lorentz_flux_hBx_bx :38-60)
+            double ut = sym4(RAW(s_u, a - 1, b), RAW(s_u, a, b), RAW(s_u, a + 1, b), RAW(s_u, a + 2, b));
+            FXc(s_Fuu, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_u, a + 1, b), 1, ut, eps), RAW(s_h, a, b));
+            double ul = 0.5 * (Bf(s_hBx, a, b) + Bf(s_hBx, a + 1, b));
+            double Lq = third(Bf(s_Bx, a + 1, b), Bf(s_Bx, a, b), Bf(s_Bx, a - 1, b));
+            double Rq = thirdR(Bf(s_Bx, a + 2, b), Bf(s_Bx, a + 1, b), Bf(s_Bx, a, b));
+            FXc(s_Lxx, a, b) = p.dy * upwind_sel(ul, Lq, Rq);
+        };
+        auto flux_uv = [&](int a, int b) {      // ffc: F_uv and Lxy (advective_lorentz_flux_hBx_by :86-108)
+            int gjf = p.gj0 + j0 + (b - 3);
+            double u2 = sym2(RAW(s_u, a, b - 1), RAW(s_u, a, b));
+            double u4 = sym4(RAW(s_u, a, b - 2), RAW(s_u, a, b - 1), RAW(s_u, a, b), RAW(s_u, a, b + 1));
+            double ut = ybuf(by, gjf, 2, NyG) ? u2 : u4;
+            FX3(s_Fuv, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_v, a, b), 1, ut, eps), HF(a, b));
+            double ul = 0.5 * (Bf(s_hBx, a, b - 1) + Bf(s_hBx, a, b));
+            double Lq = third(Bf(s_By, a, b), Bf(s_By, a - 1, b), Bf(s_By, a - 2, b));
+            double Rq = thirdR(Bf(s_By, a + 1, b), Bf(s_By, a, b), Bf(s_By, a - 1, b));
+            FX3(s_Lxy, a, b) = p.dy * upwind_sel(ul, Lq, Rq);
+        };
+        auto flux_tx = [&](int a, int b) {      // fcc: tracer transport flux and uh/ℑx h
+            double vel = RAW(s_u, a, b), hx = Bf(s_hx, a, b);
 #if SWMHD_STRICT
-                FX3(s_Tx, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps), hx);
-                FX3(s_uq, a, b) = fdiv(vel, hx);
+            FX3(s_Tx, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps), hx);
+            FX3(s_uq, a, b) = fdiv(vel, hx);
 #else
-                double rhx = frcp(hx);
-                FX3(s_Tx, a, b) = (p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps)) * rhx;
-                FX3(s_uq, a, b) = vel * rhx;
+            double rhx = frcp(hx);
+            FX3(s_Tx, a, b) = (p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps)) * rhx;
+            FX3(s_uq, a, b) = vel * rhx;
 #endif
-            } else if (t < 3 * NXF + NYF) {     // ffc (i, j0..j0+TY): F_vu and Lyx
-                int q = t - 3 * NXF;
-                int a = 3 + q % YP, b = 3 + q / YP;
-                int gjf = p.gj0 + j0 + (b - 3);
-                double vt = sym4(RAW(s_v, a - 2, b), RAW(s_v, a - 1, b), RAW(s_v, a, b), RAW(s_v, a + 1, b));
-                FY3(s_Fvu, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_u, a, b), W, vt, eps, ybuf(by, gjf, 3, NyG)), HF(a, b));
-                // advective_lorentz_flux_hBy_bx :62-84 with its Bounded-y edge branches
-                double vl = 0.5 * (Bf(s_hBy, a - 1, b) + Bf(s_hBy, a, b));
-                double L3 = third(Bf(s_Bx, a, b), Bf(s_Bx, a, b - 1), Bf(s_Bx, a, b - 2));
-                double R3 = thirdR(Bf(s_Bx, a, b + 1), Bf(s_Bx, a, b), Bf(s_Bx, a, b - 1));
-                double L1 = Bf(s_Bx, a, b - 1), R1 = Bf(s_Bx, a, b);
-                double Lq = L3, Rq = R3;
-                if (by) {
-                    if (gjf == 1) { Lq = R1; Rq = R1; } else if (gjf == 2) { Lq = L1; Rq = R3; }
-                    else if (gjf == NyG) { Lq = L3; Rq = R1; } else if (gjf == NyG + 1) { Lq = L1; Rq = L1; }
-                }
-                FY3(s_Lyx, a, b) = p.dx * upwind_sel(vl, Lq, Rq);
-            } else if (t < 3 * NXF + 2 * NYF) { // ccc (i, j0-1..j0+TY-1): F_vv and Lyy
-                int q = t - 3 * NXF - NYF;
-                int a = 3 + q % YP, b = 2 + q / YP;
-                int gjc = p.gj0 + j0 + (b - 3);                     // global cell row
-                double vt = ybuf(by, gjc + 1, 2, NyG + 1) ? sym2(RAW(s_v, a, b), RAW(s_v, a, b + 1))
-                                                          : sym4(RAW(s_v, a, b - 1), RAW(s_v, a, b), RAW(s_v, a, b + 1), RAW(s_v, a, b + 2));
-                FYc(s_Fvv, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_v, a, b + 1), W, vt, eps, ybuf(by, gjc + 1, 3, NyG + 1)), RAW(s_h, a, b));
-                // advective_lorentz_flux_hBy_by :110-132
-                double vl = 0.5 * (Bf(s_hBy, a, b) + Bf(s_hBy, a, b + 1));
-                double L3 = third(Bf(s_By, a, b + 1), Bf(s_By, a, b), Bf(s_By, a, b - 1));
-                double R3 = thirdR(Bf(s_By, a, b + 2), Bf(s_By, a, b + 1), Bf(s_By, a, b));
-                double L1 = Bf(s_By, a, b), R1 = Bf(s_By, a, b + 1);
-                double Lq = L3, Rq = R3;
-                if (by) {
-                    if (gjc == 0) { Lq = R1; Rq = R1; } else if (gjc == 1) { Lq = L1; Rq = R3; }
-                    else if (gjc == NyG - 1) { Lq = L3; Rq = R1; } else if (gjc == NyG) { Lq = L1; Rq = L1; }
-                }
-                FYc(s_Lyy, a, b) = p.dx * upwind_sel(vl, Lq, Rq);
-            } else if (t < 3 * NXF + 3 * NYF) { // cfc (i, j0..j0+TY): tracer transport flux, vh/ℑy h
-                int q = t - 3 * NXF - 2 * NYF;
-                int a = 3 + q % YP, b = 3 + q / YP;
-                int gjf = p.gj0 + j0 + (b - 3);
-                double vel = RAW(s_v, a, b), hy = Bf(s_hy, a, b);
+        };
+        auto flux_vu = [&](int a, int b) {      // ffc: F_vu and Lyx (advective_lorentz_flux_hBy_bx :62-84 with edge branches)
+            int gjf = p.gj0 + j0 + (b - 3);
+            double vt = sym4(RAW(s_v, a - 2, b), RAW(s_v, a - 1, b), RAW(s_v, a, b), RAW(s_v, a + 1, b));
+            FY3(s_Fvu, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_u, a, b), W, vt, eps, ybuf(by, gjf, 3, NyG)), HF(a, b));
+            double vl = 0.5 * (Bf(s_hBy, a - 1, b) + Bf(s_hBy, a, b));
+            double L3 = third(Bf(s_Bx, a, b), Bf(s_Bx, a, b - 1), Bf(s_Bx, a, b - 2));
+            double R3 = thirdR(Bf(s_Bx, a, b + 1), Bf(s_Bx, a, b), Bf(s_Bx, a, b - 1));
+            double L1 = Bf(s_Bx, a, b - 1), R1 = Bf(s_Bx, a, b);
+            double Lq = L3, Rq = R3;
+            if (by) {
+                if (gjf == 1) { Lq = R1; Rq = R1; } else if (gjf == 2) { Lq = L1; Rq = R3; }
+                else if (gjf == NyG) { Lq = L3; Rq = R1; } else if (gjf == NyG + 1) { Lq = L1; Rq = L1; }
+            }
+            FY3(s_Lyx, a, b) = p.dx * upwind_sel(vl, Lq, Rq);
+        };
+        auto flux_vv = [&](int a, int b) {      // ccc: F_vv and Lyy (advective_lorentz_flux_hBy_by :110-132)
+            int gjc = p.gj0 + j0 + (b - 3);                         // global cell row
+            double v2 = sym2(RAW(s_v, a, b), RAW(s_v, a, b + 1));
+            double v4 = sym4(RAW(s_v, a, b - 1), RAW(s_v, a, b), RAW(s_v, a, b + 1), RAW(s_v, a, b + 2));
+            double vt = ybuf(by, gjc + 1, 2, NyG + 1) ? v2 : v4;
+            FYc(s_Fvv, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_v, a, b + 1), W, vt, eps, ybuf(by, gjc + 1, 3, NyG + 1)), RAW(s_h, a, b));
+            double vl = 0.5 * (Bf(s_hBy, a, b) + Bf(s_hBy, a, b + 1));
+            double L3 = third(Bf(s_By, a, b + 1), Bf(s_By, a, b), Bf(s_By, a, b - 1));
+            double R3 = thirdR(Bf(s_By, a, b + 2), Bf(s_By, a, b + 1), Bf(s_By, a, b));
+            double L1 = Bf(s_By, a, b), R1 = Bf(s_By, a, b + 1);
+            double Lq = L3, Rq = R3;
+            if (by) {
+                if (gjc == 0) { Lq = R1; Rq = R1; } else if (gjc == 1) { Lq = L1; Rq = R3; }
+                else if (gjc == NyG - 1) { Lq = L3; Rq = R1; } else if (gjc == NyG) { Lq = L1; Rq = L1; }
+            }
+            FYc(s_Lyy, a, b) = p.dx * upwind_sel(vl, Lq, Rq);
+        };
+        auto flux_ty = [&](int a, int b) {      // cfc: tracer transport flux and vh/ℑy h
+            int gjf = p.gj0 + j0 + (b - 3);
+            double vel = RAW(s_v, a, b), hy = Bf(s_hy, a, b);
 #if SWMHD_STRICT
-                FY3(s_Ty, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG)), hy);
-                FY3(s_vq, a, b) = fdiv(vel, hy);
+            FY3(s_Ty, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG)), hy);
+            FY3(s_vq, a, b) = fdiv(vel, hy);
 #else
-                double rhy = frcp(hy);
-                FY3(s_Ty, a, b) = (p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG))) * rhy;
-                FY3(s_vq, a, b) = vel * rhy;
+            double rhy = frcp(hy);
+            FY3(s_Ty, a, b) = (p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG))) * rhy;
+            FY3(s_vq, a, b) = vel * rhy;
 #endif
-            } else if constexpr (DIAG) {
-                int q = t - 3 * NXF - 3 * NYF;
+        };
+        flux_uu(li - 1, lj); flux_uv(li, lj); flux_tx(li, lj);
+        flux_vu(li, lj); flux_vv(li, lj - 1); flux_ty(li, lj);
+        if (tid < 32) {                                             // north row
+            flux_vu(3 + tid, TY + 3); flux_vv(3 + tid, TY + 2); flux_ty(3 + tid, TY + 3);
+        } else if (tid < 32 + TY) {                                 // east column
+            const int b = 3 + (tid - 32);
+            flux_uu(TX + 2, b); flux_uv(TX + 3, b); flux_tx(TX + 3, b);
+        }
+        if constexpr (DIAG) {
+            for (int q = tid; q < NDG; q += NT) {
                 if (q < YP * YR) {
                     int a = 3 + q % YP, b = 3 + q / YP;
                     double bx = fdiv(-DIVDY(RAW(s_A, a, b) - RAW(s_A, a, b - 1)), Bf(s_hy, a, b));
@@ -657,7 +757,7 @@ __global__ void __launch_bounds__(NT, 3) substage_kernel(const KParams p) {
             md = fabs(DIVDX(hBx(li + 1, lj) - hBx(li, lj)) + DIVDY(hBy(li, lj + 1) - hBy(li, lj)));
             if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) nf = 1.0;
         }
-        __shared__ double red[NDIAG][NT / 32];
+        __shared__ double red[NDIAG][NT / 32];   // guarded by the end-of-tile barrier
         const int lane = tid & 31, wid = tid >> 5;
         double r[NDIAG] = {warp_sum(ke), warp_sum(me), warp_sum(pe), warp_sum(sh), warp_max(mu),
                            warp_max(mA), warp_max(mh), warp_max(md), warp_sum(nf)};
@@ -668,24 +768,40 @@ __global__ void __launch_bounds__(NT, 3) substage_kernel(const KParams p) {
             double acc = red[tid][0];
             const bool is_max = (tid >= 4 && tid <= 7);
             for (int w = 1; w < NT / 32; w++) acc = is_max ? fmax(acc, red[tid][w]) : acc + red[tid][w];
-            const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
-            p.diag[blk * NDIAG + tid] = acc;          // slot 6 holds max(-h) = -min h
+            p.diag[(size_t)tile * NDIAG + tid] = acc;  // slot 6 holds max(-h) = -min h
         }
     }
+    __syncthreads();   // end of tile: derived arrays and this raw stage may be overwritten
+  }
 }
 
+template <int FORM, int STAGE, bool DIAG, bool TMA>
+cudaError_t launch_cfg(const KParams &p, cudaStream_t st) {
+    constexpr int NSTG = (TMA && FORM == 0) ? 2 : 1;        // FORM 1 needs its shared memory for 3 CTAs/SM
+    constexpr size_t bytes = 128 + ((size_t)NSTG * 4 * SZP + SmemLayout<FORM, DIAG>::total) * sizeof(double) + 16;
+    auto kern = substage_kernel<FORM, STAGE, DIAG, TMA, NSTG>;
+    static int max_ctas = 0;
+    if (max_ctas == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, bytes);
+        if (e != cudaSuccess) return e;
+        if (occ < 1) occ = 1;
+        max_ctas = occ * sms;
+    }
+    const int ntiles = ((p.Nx + TX - 1) / TX) * p.tile_rows;
+    static int persist = -1;
+    if (persist < 0) { const char *e = getenv("SWMHD_PERSISTENT"); persist = e ? atoi(e) : 0; }
+    const int grid = (!persist || ntiles < max_ctas) ? ntiles : max_ctas;
+    kern<<<grid, NT, bytes, st>>>(p);
+    return cudaGetLastError();
+}
 template <int FORM, int STAGE, bool DIAG>
 cudaError_t launch_one(const KParams &p, cudaStream_t st) {
-    constexpr size_t bytes = (size_t)SmemLayout<FORM, DIAG>::total * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(substage_kernel<FORM, STAGE, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    dim3 grid((p.Nx + TX - 1) / TX, p.tile_rows);
-    substage_kernel<FORM, STAGE, DIAG><<<grid, NT, bytes, st>>>(p);
-    return cudaGetLastError();
+    return p.use_tma ? launch_cfg<FORM, STAGE, DIAG, true>(p, st) : launch_cfg<FORM, STAGE, DIAG, false>(p, st);
 }
 
 } // namespace

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -18,6 +19,8 @@ struct swmhd_ctx {
     int rows[4];
     size_t len[4];
     double *U[2][4];
+    CUtensorMap tmap[2][4];     // TMA descriptors of U[b][k]: 2-D (P x rows) FP64, box (TX+6) x (TY+6)
+    int use_tma;
     double *G[4];
     int cur;                    // U[cur] = current state
     double *d_partials, *d_diag; // diag partials; d_diag holds NDIAG doubles per slot
@@ -36,6 +39,32 @@ struct swmhd_ctx {
 };
 
 static thread_local std::string g_create_err;
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency,
+// so the library still loads on a machine without a driver).
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool encode_field_map(CUtensorMap *tm, double *base, int P, int rows, int box_w, int box_h) {
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess || !ptr) {
+            cudaGetLastError();
+            return false;
+        }
+        fn = (encode_tiled_fn)ptr;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)P, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)P * sizeof(double)};      // bytes between rows (multiple of 16)
+    cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
 
 #define CK(call)                                                                              \
     do {                                                                                      \
@@ -116,6 +145,12 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
         if ((e = cudaMalloc(&ctx->G[k], bytes)) != cudaSuccess) return bail("cudaMalloc tendency", e);
         if ((e = cudaMemset(ctx->G[k], 0, bytes)) != cudaSuccess) return bail("cudaMemset", e);
     }
+    // TMA tile loads need a 16-byte row pitch (even Nx); otherwise the kernels use plain loads
+    ctx->use_tma = (ctx->P % 2 == 0) ? 1 : 0;
+    for (int b = 0; b < 2 && ctx->use_tma; b++)
+        for (int k = 0; k < 4 && ctx->use_tma; k++)
+            if (!encode_field_map(&ctx->tmap[b][k], ctx->U[b][k], ctx->P, ctx->rows[k], ctx->tx + 6, ctx->ty + 6)) ctx->use_tma = 0;
+    if (getenv("SWMHD_NO_TMA")) ctx->use_tma = 0;
     ctx->nblocks_diag = diag_blocks(ctx->Nx, ctx->Ny);
     ctx->ntiles = ((ctx->Nx + ctx->tx - 1) / ctx->tx) * ctx->ntr;
     if (ctx->ntiles > ctx->nblocks_diag) ctx->nblocks_diag = ctx->ntiles;   // d_partials serves both diag paths
@@ -217,6 +252,9 @@ static KParams kparams(swmhd_ctx *ctx, double dt, int stage) {
         p.G[k] = ctx->G[k];
     }
     p.diag = nullptr;
+    p.use_tma = ctx->use_tma;
+    if (ctx->use_tma)
+        for (int k = 0; k < 4; k++) p.tm[k] = ctx->tmap[ctx->cur][k];
     return p;
 }
 

@@ -134,3 +134,16 @@ def test_fused_step_diagnostics(kind, arith):
         assert abs(dg[n]["max_abs_u"] - do["max_abs_u"]) <= 1e-15 * max(1.0, do["max_abs_u"])
         assert abs(dg[n]["max_abs_div_hB"] - do["max_abs_div_hB"]) < 1e-13
         O.step(cfg, U, 0.004, 1)
+
+
+@pytest.mark.parametrize("kind", ["J", "D"])
+def test_ragged_and_odd_sizes_strict(kind):
+    """Odd Nx (row pitch not a multiple of 16 B -> plain-load path instead of TMA) and sizes that
+    are not multiples of the 32x8 tile."""
+    for (N, Ny) in [(65, 43), (70, 50)]:
+        g, cfg, U = make_case(kind, N, Ny=Ny, arith=abi.ARITH_STRICT, perturb=13)
+        Ug = run_gpu(cfg, U, 0.004, 2)
+        O.fill_halos(cfg, U)
+        O.step(cfg, U, 0.004, 2)
+        for k in range(4):
+            assert np.array_equal(Ug[k], U[k]), (N, Ny, k)

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt 2>&1
-python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.log
-cat gpurun_out/pytest_gpu.log
-python tools/quick_bench.py 1024 4096 2>&1 | tee gpurun_out/quick_bench.log
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+echo "--- persistent TMA"; python tools/quick_bench.py 4096 2>&1 | grep fast
+echo "--- nonpersistent TMA"; SWMHD_PERSISTENT=0 python tools/quick_bench.py 4096 2>&1 | grep fast
+echo "--- nonpersistent NO_TMA"; SWMHD_PERSISTENT=0 SWMHD_NO_TMA=1 python tools/quick_bench.py 4096 2>&1 | grep fast
