@@ -147,3 +147,36 @@ def test_ragged_and_odd_sizes_strict(kind):
         O.step(cfg, U, 0.004, 2)
         for k in range(4):
             assert np.array_equal(Ug[k], U[k]), (N, Ny, k)
+
+
+@pytest.mark.parametrize("kind", ["J", "D", "BJ", "BD"])
+def test_slab_api_single_rank_equals_step(kind):
+    """The multi-GPU entry points (edges -> interior -> finish on two streams) on one slab must give
+    exactly what swmhd_step gives."""
+    from swmhd_b200.distributed import SlabModel
+    g, cfg, U = make_case(kind, 96, Ny=80, arith=abi.ARITH_FAST, perturb=17)
+    a = run_gpu(cfg, U, 0.004, 3)
+    sm = SlabModel(cfg, rank=0, world=1, device=0)
+    sm.set_state(U)
+    sm.fill_halos()
+    sm.step(0.004, 3)
+    sm.synchronize()
+    b = sm.get_state()
+    assert abs(sm.ctx.time - 3 * 0.004) < 1e-15 and sm.ctx.iteration == 3
+    sm.close()
+    for k in range(4):
+        assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("kind", ["BJ", "BD"])
+@pytest.mark.parametrize("arith", [abi.ARITH_STRICT, abi.ARITH_FAST])
+def test_bounded_y_matches_oracle(kind, arith):
+    g, cfg, U = make_case(kind, 72, Ny=56, arith=arith, perturb=19)
+    Ug = run_gpu(cfg, U, 0.004, 5)
+    O.fill_halos(cfg, U)
+    O.step(cfg, U, 0.004, 5)
+    for k in range(4):
+        if arith == abi.ARITH_STRICT:
+            assert np.array_equal(Ug[k], U[k]), (k, np.abs(Ug[k] - U[k]).max())
+        else:
+            assert rel_l2(g, Ug[k], U[k], k) <= 5e-12, k
