@@ -19,7 +19,8 @@ __global__ void halo_kernel(const HaloParams p) {
     const int nxw = nrow > 0 ? nrow * 6 : 0;
     if (t < nxw) {                       // periodic x wrap of parent row r
         int r = p.j_lo + t / 6, c = t % 6;
-        if (r >= p.rows[k]) return;
+        if (r >= p.rows[k] || r < 3 || r > Ny + 2) return;     // interior rows only: halo rows belong to the y part
+        if (k == 1 && p.by && p.y_mode == 2 && p.first && r == 3) return;   // wall row of v: zeroed below
         int dst = c < 3 ? c : Nx + c;    // 0,1,2 | Nx+3,Nx+4,Nx+5
         int src = c < 3 ? Nx + c : c;    // Nx..Nx+2 | 3,4,5
         a[(size_t)r * P + dst] = a[(size_t)r * P + src];

@@ -274,7 +274,7 @@ static void tick(swmhd_ctx *ctx, double dt, int stage) {
 extern "C" int swmhd_fill_halos(swmhd_ctx *ctx) {
     if (!ctx) return SWMHD_ERR_ARG;
     CK(cudaSetDevice(ctx->cfg.device));
-    HaloParams h = halo_params(ctx, ctx->U[ctx->cur], 3, ctx->Ny + 2 + (ctx->cfg.topo_y == SWMHD_BOUNDED ? 1 : 0), true);
+    HaloParams h = halo_params(ctx, ctx->U[ctx->cur], 3, ctx->Ny + 2, true);
     ctx->launches++;
     CK(launch_halo(h, ctx->main));
     CK(cudaStreamSynchronize(ctx->main));
