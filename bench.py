@@ -294,8 +294,7 @@ def run_native(args):
         sm = SlabModel(cfg_g, rank, world, local)
         sm.set_state(U0)
         sm.fill_halos()
-        for _ in range(W):
-            sm.diagnostics(); sm.step(dt, 1)
+        sm.step_diag(dt, W)
         sm.synchronize()
         dist.barrier(); torch.cuda.synchronize()
         if sampler:
@@ -304,14 +303,15 @@ def run_native(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(sm.main):
             e0.record(sm.main)
-        finite = True
-        for _ in range(K):
-            d = sm.diagnostics()
-            finite = finite and bool(d["all_finite"])
-            sm.step(dt, 1)
+        sm.ctx.sync()
+        for n in range(K):                       # diagnostics every step, fused in the stage-1 kernels
+            sm.ctx.arm_diag(n % 1024)
+            for stage in (1, 2, 3):
+                sm.substage(dt, stage)
         with torch.cuda.stream(sm.main):
             e1.record(sm.main)
         sm.synchronize(); torch.cuda.synchronize()
+        finite = all(d["all_finite"] for d in sm.ctx.get_diag_slots(0, min(K, 1024)))
         ms_local = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
         dist.barrier()
         dist.all_reduce(ms_local, op=dist.ReduceOp.MAX)

@@ -162,6 +162,12 @@ int  swmhd_substage_finish(swmhd_ctx *ctx, int stage);              /* swap buff
 int  swmhd_exchange_rows(swmhd_ctx *ctx, int field, int which,
                          void **dev_ptr, int *nrows, size_t *row_doubles);
 int  swmhd_sync(swmhd_ctx *ctx);
+/* Slab diagnostics without a host round trip per step: arm a slot (0..1023) and the next stage-1
+   substage (edges + interior) also evaluates the diagnostics of the state it starts from, fused in
+   the substage kernels; read any number of slots later.  Values are slab partials scaled by the
+   GLOBAL normalisation: sums add over ranks, max/min combine. */
+int  swmhd_arm_diag(swmhd_ctx *ctx, int slot);
+int  swmhd_get_diag_slots(swmhd_ctx *ctx, int first, int count, swmhd_diag *out);
 
 /* bookkeeping for bench.py: kernels launched since create, and device-side
    duration of the last swmhd_step call measured with CUDA events (ms).     */

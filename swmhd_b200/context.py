@@ -141,6 +141,14 @@ class Context:
         self._ck(self.lib.swmhd_exchange_rows(self._h, field, which, C.byref(p), C.byref(n), C.byref(w)))
         return p.value, n.value, w.value
 
+    def arm_diag(self, slot):
+        self._ck(self.lib.swmhd_arm_diag(self._h, int(slot)))
+
+    def get_diag_slots(self, first, count):
+        arr = (abi.Diag * count)()
+        self._ck(self.lib.swmhd_get_diag_slots(self._h, int(first), int(count), arr))
+        return [d.as_dict() for d in arr]
+
     def sync(self):
         self._ck(self.lib.swmhd_sync(self._h))
 

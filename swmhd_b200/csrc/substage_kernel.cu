@@ -768,7 +768,7 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             double acc = red[tid][0];
             const bool is_max = (tid >= 4 && tid <= 7);
             for (int w = 1; w < NT / 32; w++) acc = is_max ? fmax(acc, red[tid][w]) : acc + red[tid][w];
-            p.diag[(size_t)tile * NDIAG + tid] = acc;  // slot 6 holds max(-h) = -min h
+            p.diag[((size_t)p.tile_row0 * tiles_x + tile) * NDIAG + tid] = acc;  // slot 6 holds max(-h) = -min h
         }
     }
     __syncthreads();   // end of tile: derived arrays and this raw stage may be overwritten

@@ -35,6 +35,8 @@ struct swmhd_ctx {
     int tx, ty, ntr, n_last;    // tile geometry: tile rows, tile rows in the north edge group
     bool in_substage;
     double pending_dt;
+    int armed_slot;             // >= 0: the next stage-1 slab substage also produces diagnostics into this slot
+    int pending_slot;
     std::string err;
 };
 
@@ -121,7 +123,7 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
         ctx->len[k] = (size_t)ctx->P * ctx->rows[k];
         ctx->U[0][k] = ctx->U[1][k] = ctx->G[k] = nullptr;
     }
-    ctx->cur = 0; ctx->time = 0; ctx->iter = 0; ctx->launches = 0; ctx->last_ms = 0; ctx->in_substage = false;
+    ctx->cur = 0; ctx->time = 0; ctx->iter = 0; ctx->launches = 0; ctx->last_ms = 0; ctx->in_substage = false; ctx->armed_slot = -1; ctx->pending_slot = -1;
     ctx->d_partials = ctx->d_diag = nullptr; ctx->main = ctx->edge = nullptr; ctx->own_streams = false;
     ctx->ev0 = ctx->ev1 = ctx->ev_edge = ctx->ev_main = nullptr;
     substage_tile(&ctx->tx, &ctx->ty);
@@ -458,6 +460,12 @@ extern "C" int swmhd_substage_edges(swmhd_ctx *ctx, double dt, int stage) {
     CK(cudaEventRecord(ctx->ev_main, ctx->main));
     CK(cudaStreamWaitEvent(ctx->edge, ctx->ev_main, 0));
     KParams p = kparams(ctx, dt, stage);
+    ctx->pending_slot = -1;
+    if (stage == 1 && ctx->armed_slot >= 0) {
+        p.diag = ctx->d_partials;
+        ctx->pending_slot = ctx->armed_slot;
+        ctx->armed_slot = -1;
+    }
     const int ntr = ctx->ntr, nl = ctx->n_last;
     if (ntr <= 1 + nl) {            // slab too thin to split: everything is "edge"
         CK(launch_substage(ctx, p, stage, ctx->edge));
@@ -495,6 +503,7 @@ extern "C" int swmhd_substage_interior(swmhd_ctx *ctx, double dt, int stage) {
     const int ntr = ctx->ntr, nl = ctx->n_last;
     if (ntr > 1 + nl) {
         KParams p = kparams(ctx, dt, stage);
+        if (stage == 1 && ctx->pending_slot >= 0) p.diag = ctx->d_partials;
         p.tile_row0 = 1; p.tile_rows = ntr - nl - 1;
         CK(launch_substage(ctx, p, stage, ctx->main));
         HaloParams h = halo_params(ctx, ctx->U[1 - ctx->cur], 3 + ctx->ty, 3 + (ntr - nl) * ctx->ty - 1, false);
@@ -509,6 +518,11 @@ extern "C" int swmhd_substage_finish(swmhd_ctx *ctx, int stage) {
     if (!ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "no substage in flight");
     CK(cudaSetDevice(ctx->cfg.device));
     CK(cudaStreamWaitEvent(ctx->main, ctx->ev_edge, 0));
+    if (ctx->pending_slot >= 0) {       // fold the per-tile partials of edges + interior (fixed order)
+        ctx->launches++;
+        CK(launch_diag_final(ctx->d_partials, ctx->ntiles, ctx->d_diag + (size_t)ctx->pending_slot * NDIAG, ctx->main));
+        ctx->pending_slot = -1;
+    }
     ctx->cur = 1 - ctx->cur;
     ctx->in_substage = false;
     if (stage < 1 || stage > 3) return fail(ctx, SWMHD_ERR_ARG, "stage must be 1, 2 or 3");
@@ -525,6 +539,25 @@ extern "C" int swmhd_exchange_rows(swmhd_ctx *ctx, int field, int which, void **
     *dev_ptr = (void *)(ctx->U[buf][field] + (size_t)row * ctx->P);
     *nrows = 3;
     *row_doubles = (size_t)ctx->P;
+    return SWMHD_OK;
+}
+
+extern "C" int swmhd_arm_diag(swmhd_ctx *ctx, int slot) {
+    if (!ctx) return SWMHD_ERR_ARG;
+    if (slot < 0 || slot >= ctx->diag_slots) return fail(ctx, SWMHD_ERR_ARG, "diag slot out of range");
+    ctx->armed_slot = slot;
+    return SWMHD_OK;
+}
+
+extern "C" int swmhd_get_diag_slots(swmhd_ctx *ctx, int first, int count, swmhd_diag *out) {
+    if (!ctx || !out) return SWMHD_ERR_ARG;
+    if (first < 0 || count < 0 || first + count > ctx->diag_slots) return fail(ctx, SWMHD_ERR_ARG, "diag slots out of range");
+    CK(cudaSetDevice(ctx->cfg.device));
+    std::vector<double> host((size_t)count * NDIAG);
+    CK(cudaStreamSynchronize(ctx->edge));
+    CK(cudaMemcpyAsync(host.data(), ctx->d_diag + (size_t)first * NDIAG, host.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    CK(cudaStreamSynchronize(ctx->main));
+    for (int n = 0; n < count; n++) diag_fill(ctx, &host[(size_t)n * NDIAG], &out[n]);
     return SWMHD_OK;
 }
 

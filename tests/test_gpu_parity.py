@@ -164,9 +164,17 @@ def test_slab_api_single_rank_equals_step(kind):
     sm = SlabModel(cfg, rank=0, world=1, device=0)
     sm.set_state(U)
     sm.fill_halos()
-    sm.step(0.004, 3)
+    tr = sm.step_diag(0.004, 3)
     sm.synchronize()
     b = sm.get_state()
+    ref = Context(cfg)
+    ref.set_state(U)
+    ref.fill_halos()
+    tr_ref = ref.step_diag(0.004, 3)
+    ref.close()
+    for x, y in zip(tr, tr_ref):
+        for key in ("ke", "me", "pe", "sum_h", "max_abs_u", "max_abs_A", "min_h", "max_abs_div_hB"):
+            assert abs(x[key] - y[key]) <= 1e-13 * max(1.0, abs(y[key])), key
     assert abs(sm.ctx.time - 3 * 0.004) < 1e-15 and sm.ctx.iteration == 3
     sm.close()
     for k in range(4):

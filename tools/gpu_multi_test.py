@@ -18,18 +18,20 @@ ok_all = True
 for kind, Nx, Ny in [("J", 256, 200), ("D", 256, 200), ("BJ", 128, 136), ("BD", 128, 136)]:
     g, cfg, U = make_case(kind, Nx, Ny=Ny, perturb=31)
     cfg.device = local
-    ref = Context(cfg); ref.set_state(U); ref.fill_halos(); ref.step(0.002, 4); Uref = ref.get_state(); dref = ref.diagnostics(); ref.close()
+    ref = Context(cfg); ref.set_state(U); ref.fill_halos(); tr_ref = ref.step_diag(0.002, 4); Uref = ref.get_state(); dref = ref.diagnostics(); ref.close()
     j0, ny = split_rows(Ny, world)[rank]
     extra = lambda k: 1 if (k == abi.V and cfg.topo_y == abi.BOUNDED) else 0
     sm = SlabModel(cfg, rank, world, local)
     sm.set_state([slab_of_global(U[k], j0, ny, extra(k)) for k in range(4)])
     sm.fill_halos()
-    sm.step(0.002, 4)
+    tr = sm.step_diag(0.002, 4)
     sm.synchronize()
     out = sm.get_state()
     d = sm.diagnostics()
     ok = all(np.array_equal(out[k][3:3 + ny], Uref[k][3 + j0:3 + j0 + ny]) for k in range(4))
-    dok = all(abs(d[key] - dref[key]) <= 1e-13 * max(1.0, abs(dref[key])) for key in ("ke", "me", "pe", "sum_h", "max_abs_u", "max_abs_A", "min_h"))
+    keys = ("ke", "me", "pe", "sum_h", "max_abs_u", "max_abs_A", "min_h")
+    dok = all(abs(d[key] - dref[key]) <= 1e-13 * max(1.0, abs(dref[key])) for key in keys)
+    dok = dok and all(abs(a[key] - b[key]) <= 1e-13 * max(1.0, abs(b[key])) for a, b in zip(tr, tr_ref) for key in keys)
     t = torch.tensor([int(ok), int(dok)], device=f"cuda:{local}")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
