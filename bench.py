@@ -26,7 +26,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 from pathlib import Path
 
@@ -44,8 +43,8 @@ STAGE_BYTES = (96.0, 128.0, 96.0)      # per cell: stage 1: 4R+8W, stage 2: 8R+8
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--size", type=int, default=4096, help="Nx and rows per GPU")
     ap.add_argument("--form", default="jacobian", choices=["jacobian", "divergence"])
@@ -79,30 +78,31 @@ def initial_state(grid, form, pinned=False):
     return U
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """nvidia-smi -lms sampler of SM clocks / throttle reasons running DURING the timed region."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=6)
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+            except Exception:
+                pass
         sm, reasons, mx = [], set(), None
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx = float(r[1])
             except Exception:
@@ -269,14 +269,12 @@ def run_native(args):
             h2d = sum(a.nbytes for a in U0)
             for _ in range(2):
                 M.set_b(model, **{n: U0[k] for k, n in enumerate(names)})
-                M.time_step_b(model, dt)
-                model.diagnostics()
+                M.time_step_diag_b(model, dt)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             for _ in range(ke):
                 M.set_b(model, **{n: U0[k] for k, n in enumerate(names)})   # H2D of the four haloed fields (pinned)
-                M.time_step_b(model, dt)                                     # one RK3 step
-                d = model.diagnostics()                                      # D2H of the step's result
+                d = M.time_step_diag_b(model, dt)                            # one RK3 step + D2H of its diagnostics
             torch.cuda.synchronize()
             el = time.perf_counter() - t0
             e2e = {"value": ncell * ke / el, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 9 * 8,

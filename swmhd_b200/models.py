@@ -240,11 +240,12 @@ def set_b(model: ShallowWaterModel, **kwargs):
         if name not in by_name:
             raise KeyError(f"{name} is not a field of this model ({list(by_name)})")
         f = by_name[name]
+        if isinstance(val, np.ndarray) and val.shape == f.parent.shape and val.dtype == np.float64 and val.flags["C_CONTIGUOUS"]:
+            model.ctx.set_field(f.index, val)      # a full parent array: straight H2D (fast when pinned)
+            f._stale = True
+            continue
         f._refresh()
-        if isinstance(val, np.ndarray) and val.shape == f.parent.shape:
-            f.parent[...] = val
-        else:
-            model.grid.set_interior(f.parent, f.index, val)
+        model.grid.set_interior(f.parent, f.index, val)
         model.ctx.set_field(f.index, f.parent)
     model.ctx.fill_halos()
     model._mark_stale()
@@ -254,6 +255,14 @@ def time_step_b(model: ShallowWaterModel, dt, nsteps=1):
     """`time_step!(model, Δt)`: one (or nsteps) RK3 step(s) on the device."""
     model.ctx.step(dt, nsteps)
     model._mark_stale()
+
+
+def time_step_diag_b(model: ShallowWaterModel, dt, nsteps=1):
+    """`time_step!` x nsteps that also returns, per step, the energy / progress diagnostics of the
+    state the step started from (SWMHD_example.jl:47-77), evaluated inside the stage-1 kernel."""
+    out = model.ctx.step_diag(dt, nsteps)
+    model._mark_stale()
+    return out
 
 
 # -- Simulation -------------------------------------------------------------------------------
