@@ -126,30 +126,60 @@ __global__ void __launch_bounds__(DT) diag_kernel(const DiagParams p) {
     }
 }
 
-// fixed-order final reduction (deterministic): thread t folds partials t, t+FT, ... in order,
-// then a fixed binary tree over the FT lanes.  Slots 4..7 are maxima, the rest sums.
-constexpr int FT = 1024;
-__global__ void __launch_bounds__(FT) diag_final_kernel(const double *partials, int nblocks, double *out) {
-    __shared__ double sh[FT];
-    for (int q = 0; q < NDIAG; q++) {
-        const bool is_max = (q >= 4 && q <= 7);
-        double acc = is_max ? -INFINITY : 0.0;
-        for (int b = threadIdx.x; b < nblocks; b += FT) {
-            double x = partials[(size_t)b * NDIAG + q];
-            acc = is_max ? fmax(acc, x) : acc + x;
-        }
-        sh[threadIdx.x] = acc;
-        __syncthreads();
-        for (int s = FT / 2; s > 0; s >>= 1) {
-            if (threadIdx.x < s) {
-                double x = sh[threadIdx.x + s];
-                sh[threadIdx.x] = is_max ? fmax(sh[threadIdx.x], x) : sh[threadIdx.x] + x;
+// Fixed-order two-level final reduction (deterministic for a given launch geometry): block b folds
+// the contiguous chunk b of the per-tile partials (thread-strided, then a fixed binary tree) into
+// stage[b]; the last block to finish folds stage[0..FB) the same way.  Slots 4..7 are maxima.
+constexpr int FT = 256, FB = 64;
+__device__ unsigned int g_final_ticket = 0;
+
+__device__ __forceinline__ void block_fold(double (&v)[NDIAG], double (*sh)[FT]) {
+#pragma unroll
+    for (int q = 0; q < NDIAG; q++) sh[q][threadIdx.x] = v[q];
+    __syncthreads();
+    for (int s = FT / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+#pragma unroll
+            for (int q = 0; q < NDIAG; q++) {
+                const double x = sh[q][threadIdx.x + s];
+                sh[q][threadIdx.x] = (q >= 4 && q <= 7) ? fmax(sh[q][threadIdx.x], x) : sh[q][threadIdx.x] + x;
             }
-            __syncthreads();
         }
-        if (threadIdx.x == 0) out[q] = sh[0];
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(FT) diag_final_kernel(const double *partials, int nblocks, double *stage, double *out) {
+    __shared__ double sh[NDIAG][FT];
+    __shared__ bool last;
+    const int per = (nblocks + FB - 1) / FB;
+    const int lo = blockIdx.x * per, hi = min(nblocks, lo + per);
+    double v[NDIAG];
+#pragma unroll
+    for (int q = 0; q < NDIAG; q++) v[q] = (q >= 4 && q <= 7) ? -INFINITY : 0.0;
+    for (int b = lo + threadIdx.x; b < hi; b += FT) {
+#pragma unroll
+        for (int q = 0; q < NDIAG; q++) {
+            const double x = partials[(size_t)b * NDIAG + q];
+            v[q] = (q >= 4 && q <= 7) ? fmax(v[q], x) : v[q] + x;
+        }
+    }
+    block_fold(v, sh);
+    if (threadIdx.x < NDIAG) stage[(size_t)blockIdx.x * NDIAG + threadIdx.x] = sh[threadIdx.x][0];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(&g_final_ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < NDIAG; q++) {
+        const bool is_max = (q >= 4 && q <= 7);
+        v[q] = is_max ? -INFINITY : 0.0;
+        if (threadIdx.x < FB) v[q] = stage[(size_t)threadIdx.x * NDIAG + q];
+    }
+    block_fold(v, sh);
+    if (threadIdx.x < NDIAG) out[threadIdx.x] = sh[threadIdx.x][0];
+    if (threadIdx.x == 0) g_final_ticket = 0;
 }
 
 } // namespace
@@ -169,12 +199,14 @@ int diag_blocks(int Nx, int Ny) {
 
 cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st) {
     diag_kernel<<<p.nblocks, DT, 0, st>>>(p);
-    diag_final_kernel<<<1, FT, 0, st>>>(p.partials, p.nblocks, out9);
+    diag_final_kernel<<<FB, FT, 0, st>>>(p.partials, p.nblocks, p.stage, out9);
     return cudaGetLastError();
 }
 
-cudaError_t launch_diag_final(const double *partials, int nblocks, double *out9, cudaStream_t st) {
-    diag_final_kernel<<<1, FT, 0, st>>>(partials, nblocks, out9);
+int diag_stage_doubles() { return FB * NDIAG; }
+
+cudaError_t launch_diag_final(const double *partials, int nblocks, double *stage, double *out9, cudaStream_t st) {
+    diag_final_kernel<<<FB, FT, 0, st>>>(partials, nblocks, stage, out9);
     return cudaGetLastError();
 }
 

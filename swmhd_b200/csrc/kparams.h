@@ -45,6 +45,7 @@ struct DiagParams {
     double dx, dy, g, h_ref;
     const double *U[4];
     double *partials;      // [nblocks][NDIAG]
+    double *stage;         // [diag_stage_doubles()] scratch of the two-level final reduction
     int nblocks;
 };
 
@@ -56,7 +57,8 @@ cudaError_t launch_substage_fast(const KParams &p, int form, int stage, cudaStre
 void substage_tile(int *tx, int *ty);
 cudaError_t launch_halo(const HaloParams &p, cudaStream_t st);
 cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st);
-cudaError_t launch_diag_final(const double *partials, int nblocks, double *out9, cudaStream_t st);
+cudaError_t launch_diag_final(const double *partials, int nblocks, double *stage, double *out9, cudaStream_t st);
+int diag_stage_doubles();
 int diag_blocks(int Nx, int Ny);
 
 } // namespace swmhd

@@ -749,26 +749,50 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             mu = (FORM == 0) ? fabs(uu) : fabs(fdiv(uu, 0.5 * (RAW(s_h, li - 1, lj) + hh)));
             mA = fabs(aa);
             mh = -hh;
-            // div(hB) at ccc with hBx, hBy of sw_mhd_divergence_functions.jl:142-148
+            // div(hB) at ccc with hBx, hBy of sw_mhd_divergence_functions.jl:142-148 (pure round-off: ~1e-15)
+#if SWMHD_STRICT
             auto DyA = [&](int a, int b) { return DIVDY(RAW(s_A, a, b) - RAW(s_A, a, b - 1)); };
             auto DxA = [&](int a, int b) { return DIVDX(RAW(s_A, a, b) - RAW(s_A, a - 1, b)); };
             auto hBx = [&](int a, int b) { return -avg4(DyA(a - 1, b), DyA(a, b), DyA(a - 1, b + 1), DyA(a, b + 1)); };
             auto hBy = [&](int a, int b) { return avg4(DxA(a, b - 1), DxA(a + 1, b - 1), DxA(a, b), DxA(a + 1, b)); };
             md = fabs(DIVDX(hBx(li + 1, lj) - hBx(li, lj)) + DIVDY(hBy(li, lj + 1) - hBy(li, lj)));
+#else
+            {   // telescoped ℑxy∂: hBx(a,b) = (A(a-1,b-1)+A(a,b-1)-A(a-1,b+1)-A(a,b+1))/(4dy), hBy likewise
+                const double Amm = RAW(s_A, li - 1, lj - 1), A0m = RAW(s_A, li, lj - 1), Apm = RAW(s_A, li + 1, lj - 1);
+                const double Am0 = RAW(s_A, li - 1, lj), Ap0 = RAW(s_A, li + 1, lj);
+                const double Amp = RAW(s_A, li - 1, lj + 1), A0p = RAW(s_A, li, lj + 1), App = RAW(s_A, li + 1, lj + 1);
+                const double hbx0 = (Amm + A0m) - (Amp + A0p), hbx1 = (A0m + Apm) - (A0p + App);
+                const double hby0 = (Apm + Ap0) - (Amm + Am0), hby1 = (Ap0 + App) - (Am0 + Amp);
+                md = fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy);
+            }
+#endif
             if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) nf = 1.0;
         }
-        __shared__ double red[NDIAG][NT / 32];   // guarded by the end-of-tile barrier
-        const int lane = tid & 31, wid = tid >> 5;
-        double r[NDIAG] = {warp_sum(ke), warp_sum(me), warp_sum(pe), warp_sum(sh), warp_max(mu),
-                           warp_max(mA), warp_max(mh), warp_max(md), warp_sum(nf)};
-        if (lane == 0)
-            for (int q = 0; q < NDIAG; q++) red[q][wid] = r[q];
+        // 256 -> 32 through shared memory (one add per value and thread row), then one warp finishes
+        // with shuffles: 3x fewer FP64 instructions than eight independent warp trees.
+        __shared__ double red[NDIAG][NT];          // guarded by the end-of-tile barrier
+        const double mine[NDIAG] = {ke, me, pe, sh, mu, mA, mh, md, nf};
+#pragma unroll
+        for (int q = 0; q < NDIAG; q++) red[q][tid] = mine[q];
         __syncthreads();
-        if (tid < NDIAG) {
-            double acc = red[tid][0];
-            const bool is_max = (tid >= 4 && tid <= 7);
-            for (int w = 1; w < NT / 32; w++) acc = is_max ? fmax(acc, red[tid][w]) : acc + red[tid][w];
-            p.diag[((size_t)p.tile_row0 * tiles_x + tile) * NDIAG + tid] = acc;  // slot 6 holds max(-h) = -min h
+        if (tid < 32) {
+            double r[NDIAG];
+#pragma unroll
+            for (int q = 0; q < NDIAG; q++) {
+                const bool is_max = (q >= 4 && q <= 7);
+                double acc = red[q][tid];
+#pragma unroll
+                for (int w = 1; w < NT / 32; w++) {
+                    const double x = red[q][tid + 32 * w];
+                    acc = is_max ? fmax(acc, x) : acc + x;
+                }
+                r[q] = is_max ? warp_max(acc) : warp_sum(acc);
+            }
+            if (tid == 0) {
+                double *dst = p.diag + ((size_t)p.tile_row0 * tiles_x + tile) * NDIAG;   // slot 6 = max(-h) = -min h
+#pragma unroll
+                for (int q = 0; q < NDIAG; q++) dst[q] = r[q];
+            }
         }
     }
     __syncthreads();   // end of tile: derived arrays and this raw stage may be overwritten
@@ -777,7 +801,9 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
 
 template <int FORM, int STAGE, bool DIAG, bool TMA>
 cudaError_t launch_cfg(const KParams &p, cudaStream_t st) {
-    constexpr int NSTG = (TMA && FORM == 0) ? 2 : 1;        // FORM 1 needs its shared memory for 3 CTAs/SM
+    // One raw-tile stage: with one tile per CTA (the default, non-persistent launch) the other resident
+    // CTAs hide the TMA latency; a second stage only costs registers and shared memory.
+    constexpr int NSTG = 1;
     constexpr size_t bytes = 128 + ((size_t)NSTG * 4 * SZP + SmemLayout<FORM, DIAG>::total) * sizeof(double) + 16;
     auto kern = substage_kernel<FORM, STAGE, DIAG, TMA, NSTG>;
     static int max_ctas = 0;

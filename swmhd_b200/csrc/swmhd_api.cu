@@ -23,7 +23,7 @@ struct swmhd_ctx {
     int use_tma;
     double *G[4];
     int cur;                    // U[cur] = current state
-    double *d_partials, *d_diag; // diag partials; d_diag holds NDIAG doubles per slot
+    double *d_partials, *d_diag, *d_stage; // diag partials; d_diag holds NDIAG doubles per slot
     int diag_slots;
     int nblocks_diag, ntiles;
     cudaStream_t main, edge;
@@ -124,7 +124,7 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
         ctx->U[0][k] = ctx->U[1][k] = ctx->G[k] = nullptr;
     }
     ctx->cur = 0; ctx->time = 0; ctx->iter = 0; ctx->launches = 0; ctx->last_ms = 0; ctx->in_substage = false; ctx->armed_slot = -1; ctx->pending_slot = -1;
-    ctx->d_partials = ctx->d_diag = nullptr; ctx->main = ctx->edge = nullptr; ctx->own_streams = false;
+    ctx->d_partials = ctx->d_diag = ctx->d_stage = nullptr; ctx->main = ctx->edge = nullptr; ctx->own_streams = false;
     ctx->ev0 = ctx->ev1 = ctx->ev_edge = ctx->ev_main = nullptr;
     substage_tile(&ctx->tx, &ctx->ty);
     ctx->ntr = (ctx->Ny + ctx->ty - 1) / ctx->ty;
@@ -159,6 +159,7 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
     ctx->diag_slots = 1024;
     if ((e = cudaMalloc(&ctx->d_partials, (size_t)ctx->nblocks_diag * NDIAG * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
     if ((e = cudaMalloc(&ctx->d_diag, (size_t)ctx->diag_slots * NDIAG * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
+    if ((e = cudaMalloc(&ctx->d_stage, (size_t)diag_stage_doubles() * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
     int lo, hi;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if ((e = cudaStreamCreateWithPriority(&ctx->main, cudaStreamNonBlocking, lo)) != cudaSuccess) return bail("stream", e);
@@ -179,7 +180,7 @@ extern "C" void swmhd_destroy(swmhd_ctx *ctx) {
     for (int k = 0; k < 4; k++) {
         cudaFree(ctx->U[0][k]); cudaFree(ctx->U[1][k]); cudaFree(ctx->G[k]);
     }
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_diag);
+    cudaFree(ctx->d_partials); cudaFree(ctx->d_diag); cudaFree(ctx->d_stage);
     if (ctx->own_streams) {
         if (ctx->main) cudaStreamDestroy(ctx->main);
         if (ctx->edge) cudaStreamDestroy(ctx->edge);
@@ -292,7 +293,7 @@ static int substage_async(swmhd_ctx *ctx, double dt, int stage, cudaEvent_t e0 =
     if (e1) CK(cudaEventRecord(e1, ctx->main));
     if (diag_slot >= 0 && stage == 1) {
         ctx->launches++;
-        CK(launch_diag_final(ctx->d_partials, ctx->ntiles, ctx->d_diag + (size_t)diag_slot * NDIAG, ctx->main));
+        CK(launch_diag_final(ctx->d_partials, ctx->ntiles, ctx->d_stage, ctx->d_diag + (size_t)diag_slot * NDIAG, ctx->main));
     }
     HaloParams h = halo_params(ctx, ctx->U[1 - ctx->cur], 3, ctx->Ny + 2, true);
     ctx->launches++;
@@ -319,7 +320,7 @@ static int diag_async(swmhd_ctx *ctx, int slot) {
     d.Nx = ctx->Nx; d.Ny = ctx->Ny; d.P = ctx->P; d.form = c.formulation;
     d.dx = c.dx; d.dy = c.dy; d.g = c.g; d.h_ref = c.h_ref;
     for (int k = 0; k < 4; k++) d.U[k] = ctx->U[ctx->cur][k];
-    d.partials = ctx->d_partials; d.nblocks = ctx->nblocks_diag;
+    d.partials = ctx->d_partials; d.nblocks = diag_blocks(ctx->Nx, ctx->Ny); d.stage = ctx->d_stage;
     ctx->launches += 2;
     CK(launch_diag(d, ctx->d_diag + (size_t)slot * NDIAG, ctx->main));
     return SWMHD_OK;
@@ -520,7 +521,7 @@ extern "C" int swmhd_substage_finish(swmhd_ctx *ctx, int stage) {
     CK(cudaStreamWaitEvent(ctx->main, ctx->ev_edge, 0));
     if (ctx->pending_slot >= 0) {       // fold the per-tile partials of edges + interior (fixed order)
         ctx->launches++;
-        CK(launch_diag_final(ctx->d_partials, ctx->ntiles, ctx->d_diag + (size_t)ctx->pending_slot * NDIAG, ctx->main));
+        CK(launch_diag_final(ctx->d_partials, ctx->ntiles, ctx->d_stage, ctx->d_diag + (size_t)ctx->pending_slot * NDIAG, ctx->main));
         ctx->pending_slot = -1;
     }
     ctx->cur = 1 - ctx->cur;
