@@ -276,9 +276,11 @@ template <bool DIAG> struct SmemLayout<1, DIAG> {
 // plain-load path (odd Nx: the row pitch is not a multiple of 16 B).
 template <int FORM, int STAGE, bool DIAG, bool TMA, int NSTG>
 __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_constant__ KParams p) {
-    extern __shared__ unsigned char smem_bytes[];
+    // 128-byte aligned for the TMA destination; used directly (no integer round-up) so that the compiler
+    // keeps the shared address space and emits LDS/STS instead of generic LD/ST.
+    extern __shared__ __align__(128) unsigned char smem_bytes[];
     using L = SmemLayout<FORM, DIAG>;
-    double *const raw0 = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(smem_bytes) + 127) & ~uintptr_t(127));
+    double *const raw0 = reinterpret_cast<double *>(smem_bytes);
     double *const smem = raw0 + NSTG * 4 * SZP;             // derived / flux arrays
     uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + L::total);
     const int tid = threadIdx.x;
