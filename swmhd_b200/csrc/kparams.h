@@ -17,6 +17,7 @@ struct KParams {
     int gj0, NyG;        // global row of local row j is gj0 + j; global Ny
     int by;              // topo_y == Bounded
     int tile_row0, tile_rows; // first tile-row and number of tile-rows of this launch
+    int tiles_per_cta;        // consecutive tiles one CTA processes (set by the launcher)
     int rows[4];         // parent rows per field (Ny+6, v: +1 when Bounded-y)
     double dx, dy, rdx, rdy, inv_az, g, f, eps;
     double dt, gam, zet, dtgam;  // stage coefficients; dtgam = dt*gam (stage 1)

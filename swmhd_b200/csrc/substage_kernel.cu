@@ -38,6 +38,9 @@ namespace {
 #define LAUNCH_NAME launch_substage_fast
 #endif
 
+#ifndef SWMHD_TPC_DEFAULT
+#define SWMHD_TPC_DEFAULT 4
+#endif
 #ifndef SWMHD_MINB
 #define SWMHD_MINB 3
 #endif
@@ -304,8 +307,13 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < 4; k++) tma_load_2d(dst + k * SZP, &p.tm[k], c0, c1, &mbar[stage]);
     };
+    // A CTA owns `tpc` consecutive tiles [tile_lo, tile_hi); CTAs are launched dynamically by the
+    // hardware, which keeps the resident CTAs of an SM out of phase (load / FP64 / store overlap).
+    const int tpc = p.tiles_per_cta;
+    const int tile_lo = blockIdx.x * tpc;
+    const int tile_hi = min(ntiles, tile_lo + tpc);
     if constexpr (TMA && NSTG == 2) {
-        if (tid == 0 && (int)blockIdx.x < ntiles) issue_load(blockIdx.x, 0);
+        if (tid == 0 && tile_lo < tile_hi) issue_load(tile_lo, 0);
     }
 
     // own cell of this thread (tile-local)
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
     (void)s_sqBx; (void)s_sqBy;
 
   int it = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+  for (int tile = tile_lo; tile < tile_hi; ++tile, ++it) {
     const int stg = (NSTG == 2) ? (it & 1) : 0;
     double *s_u = raw0 + stg * 4 * SZP, *s_v = s_u + SZP, *s_h = s_u + 2 * SZP, *s_A = s_u + 3 * SZP;
     const int i0 = (tile % tiles_x) * TX + 1;               // logical (1-based) first cell
@@ -329,8 +337,8 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
     if constexpr (TMA) {
         if (tid == 0) {
             if constexpr (NSTG == 2) {
-                const int nxt = tile + gridDim.x;            // prefetch: overlaps this tile's arithmetic
-                if (nxt < ntiles) issue_load(nxt, stg ^ 1);
+                const int nxt = tile + 1;                    // prefetch: overlaps this tile's arithmetic
+                if (nxt < tile_hi) issue_load(nxt, stg ^ 1);
             } else {
                 issue_load(tile, 0);
             }
@@ -805,7 +813,9 @@ template <int FORM, int STAGE, bool DIAG, bool TMA>
 cudaError_t launch_cfg(const KParams &p, cudaStream_t st) {
     // One raw-tile stage: with one tile per CTA (the default, non-persistent launch) the other resident
     // CTAs hide the TMA latency; a second stage only costs registers and shared memory.
-    constexpr int NSTG = 1;
+    // FORM 0: two raw-tile stages (the TMA load of the CTA's next tile overlaps the arithmetic of the
+    // current one); FORM 1 needs its shared memory for 3 CTAs/SM and relies on the other CTAs.
+    constexpr int NSTG = (TMA && FORM == 0) ? 2 : 1;
     constexpr size_t bytes = 128 + ((size_t)NSTG * 4 * SZP + SmemLayout<FORM, DIAG>::total) * sizeof(double) + 16;
     auto kern = substage_kernel<FORM, STAGE, DIAG, TMA, NSTG>;
     static int max_ctas = 0;
@@ -821,10 +831,13 @@ cudaError_t launch_cfg(const KParams &p, cudaStream_t st) {
         max_ctas = occ * sms;
     }
     const int ntiles = ((p.Nx + TX - 1) / TX) * p.tile_rows;
-    static int persist = -1;
-    if (persist < 0) { const char *e = getenv("SWMHD_PERSISTENT"); persist = e ? atoi(e) : 0; }
-    const int grid = (!persist || ntiles < max_ctas) ? ntiles : max_ctas;
-    kern<<<grid, NT, bytes, st>>>(p);
+    static int tpc = -1;
+    if (tpc < 0) { const char *e = getenv("SWMHD_TPC"); tpc = e ? atoi(e) : SWMHD_TPC_DEFAULT; if (tpc < 1) tpc = 1; }
+    KParams q = p;
+    q.tiles_per_cta = (NSTG == 2) ? tpc : 1;
+    const int grid = (ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
+    (void)max_ctas;
+    kern<<<grid, NT, bytes, st>>>(q);
     return cudaGetLastError();
 }
 template <int FORM, int STAGE, bool DIAG>
