@@ -780,8 +780,12 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
         }
         // 256 -> 32 through shared memory (one add per value and thread row), then one warp finishes
         // with shuffles: 3x fewer FP64 instructions than eight independent warp trees.
-        __shared__ double red[NDIAG][NT];          // guarded by the end-of-tile barrier
+        // (the scratch aliases the derived/flux arrays, which are dead once every thread has finished phase C,
+        //  so the DIAG variant keeps the 3 CTAs/SM of the plain one)
+        static_assert(NDIAG * NT <= L::o_dg, "diag scratch must fit in the derived-array region");
+        double (*red)[NT] = reinterpret_cast<double (*)[NT]>(smem);
         const double mine[NDIAG] = {ke, me, pe, sh, mu, mA, mh, md, nf};
+        __syncthreads();
 #pragma unroll
         for (int q = 0; q < NDIAG; q++) red[q][tid] = mine[q];
         __syncthreads();
