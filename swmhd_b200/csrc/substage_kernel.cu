@@ -118,42 +118,48 @@ __device__ __forceinline__ double weno5_vs(const double *qz, const double *qu, c
                       0.5 * (bu0 + bv0), 0.5 * (bu1 + bv1), 0.5 * (bu2 + bv2), eps);
 }
 #else
-// acc + k13*D^2 + k14*E^2 for the three candidate stencils (k13 = 13/12*s, k14 = 1/4*s)
-__device__ __forceinline__ void weno_beta_acc(double a, double b, double c, double d, double e, double k13, double k14,
-                                              double &c0, double &c1, double &c2) {
-    double D0 = fma(-2.0, d, c + e), E0 = fma(3.0, c, fma(-4.0, d, e));
-    double D1 = fma(-2.0, c, b + d), E1 = b - d;
-    double D2 = fma(-2.0, b, a + c), E2 = fma(3.0, c, fma(-4.0, b, a));
+// FAST WENO5-Z in difference form.  With the first differences d1..d4 of the five upwind samples
+// (a,b,c,d,e) the second differences and the E terms cost one operation each, and every candidate is
+// c + X_k/6 with X_0 = 4 d3 - d4, X_1 = d2 + 2 d3, X_2 = 5 d2 - 2 d1, so that
+//     sum(w_k p_k) = c + sum(alpha_k C_k X_k / 6) / sum(C_k alpha_k):   a correction to the upwind-side
+// cell value instead of a blend of O(1) numbers.
+// alpha_k = 1 + tau^2/c_k^2 (c_k = beta_k + eps) is multiplied through by prod(c_k^2): one division.
+struct WenoDiff { double c, d1, d2, d3, d4; };
+__device__ __forceinline__ WenoDiff weno_diffs(double a, double b, double c, double d, double e) {
+    WenoDiff w; w.c = c; w.d1 = b - a; w.d2 = c - b; w.d3 = d - c; w.d4 = e - d; return w;
+}
+// acc_k += k13 * D_k^2 + k14 * E_k^2   (k13 = 13/12 s, k14 = 1/4 s)
+__device__ __forceinline__ void weno_beta_acc(const WenoDiff &w, double k13, double k14, double &c0, double &c1, double &c2) {
+    const double D0 = w.d4 - w.d3, E0 = fma(-3.0, w.d3, w.d4);      // (c,d,e): c-2d+e, 3c-4d+e
+    const double D1 = w.d3 - w.d2, E1 = w.d2 + w.d3;               // (b,c,d): b-2c+d, -(b-d)
+    const double D2 = w.d2 - w.d1, E2 = fma(3.0, w.d2, -w.d1);     // (a,b,c): a-2b+c, a-4b+3c
     c0 = fma(k13 * D0, D0, fma(k14 * E0, E0, c0));
     c1 = fma(k13 * D1, D1, fma(k14 * E1, E1, c1));
     c2 = fma(k13 * D2, D2, fma(k14 * E2, E2, c2));
 }
-// alpha_k = C_k (1 + tau^2/c_k^2), c_k = beta_k + eps.  Multiplying numerator and denominator of
-// sum(alpha_k p_k)/sum(alpha_k) by prod(c_k^2) leaves one division:  alpha_k ~ C_k (S + tau^2 q_k),
-// S = s0 s1 s2, q_k = S/s_k, s_k = c_k^2;  C_k/6 is folded into the candidate polynomials.
-__device__ __forceinline__ double weno_blend_c(double a, double b, double c, double d, double e,
-                                               double c0, double c1, double c2) {
-    double tau = c2 - c0, t2 = tau * tau;
-    double s0 = c0 * c0, s1 = c1 * c1, s2 = c2 * c2;
-    double q2 = s0 * s1, q0 = s1 * s2, q1 = s0 * s2, S = q2 * s2;
-    double a0 = fma(t2, q0, S), a1 = fma(t2, q1, S), a2 = fma(t2, q2, S);
-    double P0 = fma(0.1, c, fma(0.25, d, -0.05 * e));                       // 0.3/6 (2c + 5d - e)
-    double P1 = fma(-0.1, b, fma(0.5, c, 0.2 * d));                         // 0.6/6 (-b + 5c + 2d)
-    double P2 = fma(1.0 / 30.0, a, fma(-7.0 / 60.0, b, (11.0 / 60.0) * c)); // 0.1/6 (2a - 7b + 11c)
-    double num = fma(a0, P0, fma(a1, P1, a2 * P2));
-    double den = fma(0.3, a0, fma(0.6, a1, 0.1 * a2));
-    return num * frcp(den);
+__device__ __forceinline__ double weno_blend_c(const WenoDiff &w, double c0, double c1, double c2) {
+    const double tau = c2 - c0, t2 = tau * tau;
+    const double s0 = c0 * c0, s1 = c1 * c1, s2 = c2 * c2;
+    const double q2 = s0 * s1, q0 = s1 * s2, q1 = s0 * s2, S = q2 * s2;
+    const double a0 = fma(t2, q0, S), a1 = fma(t2, q1, S), a2 = fma(t2, q2, S);
+    const double Y0 = fma(0.2, w.d3, -0.05 * w.d4);                 // 0.3/6 (4 d3 - d4)
+    const double Y1 = fma(0.2, w.d3, 0.1 * w.d2);                   // 0.6/6 (d2 + 2 d3)
+    const double Y2 = fma(1.0 / 12.0, w.d2, (-1.0 / 30.0) * w.d1);  // 0.1/6 (5 d2 - 2 d1)
+    const double num = fma(a0, Y0, fma(a1, Y1, a2 * Y2));
+    const double den = fma(0.3, a0, fma(0.6, a1, 0.1 * a2));
+    return fma(num, frcp(den), w.c);
 }
 __device__ __forceinline__ double weno5(double a, double b, double c, double d, double e, double eps) {
+    const WenoDiff w = weno_diffs(a, b, c, d, e);
     double c0 = eps, c1 = eps, c2 = eps;
-    weno_beta_acc(a, b, c, d, e, 13.0 / 12.0, 0.25, c0, c1, c2);
-    return weno_blend_c(a, b, c, d, e, c0, c1, c2);
+    weno_beta_acc(w, 13.0 / 12.0, 0.25, c0, c1, c2);
+    return weno_blend_c(w, c0, c1, c2);
 }
 __device__ __forceinline__ double weno5_vs(const double *qz, const double *qu, const double *qv, int s, double eps) {
     double c0 = eps, c1 = eps, c2 = eps;
-    weno_beta_acc(qu[0], qu[s], qu[2 * s], qu[3 * s], qu[4 * s], 13.0 / 24.0, 0.125, c0, c1, c2);
-    weno_beta_acc(qv[0], qv[s], qv[2 * s], qv[3 * s], qv[4 * s], 13.0 / 24.0, 0.125, c0, c1, c2);
-    return weno_blend_c(qz[0], qz[s], qz[2 * s], qz[3 * s], qz[4 * s], c0, c1, c2);
+    weno_beta_acc(weno_diffs(qu[0], qu[s], qu[2 * s], qu[3 * s], qu[4 * s]), 13.0 / 24.0, 0.125, c0, c1, c2);
+    weno_beta_acc(weno_diffs(qv[0], qv[s], qv[2 * s], qv[3 * s], qv[4 * s]), 13.0 / 24.0, 0.125, c0, c1, c2);
+    return weno_blend_c(weno_diffs(qz[0], qz[s], qz[2 * s], qz[3 * s], qz[4 * s]), c0, c1, c2);
 }
 #endif
 
