@@ -568,9 +568,16 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
                 double hx = 0.5 * (RAW(s_h, a - 1, b) + RAW(s_h, a, b));
                 double hy = 0.5 * (RAW(s_h, a, b - 1) + RAW(s_h, a, b));
                 Bf(s_hBx, a, b) = hbx; Bf(s_hBy, a, b) = hby;
+#if SWMHD_STRICT
                 Bf(s_hx, a, b) = hx;   Bf(s_hy, a, b) = hy;
                 Bf(s_Bx, a, b) = fdiv(hbx, hx);
                 Bf(s_By, a, b) = fdiv(hby, hy);
+#else
+                const double rhx = frcp(hx), rhy = frcp(hy);        // FAST: s_hx / s_hy hold 1/ℑx h, 1/ℑy h
+                Bf(s_hx, a, b) = rhx;  Bf(s_hy, a, b) = rhy;
+                Bf(s_Bx, a, b) = hbx * rhx;
+                Bf(s_By, a, b) = hby * rhy;
+#endif
             } else {                                                // ℑxyᶠᶠᵃ h, a in [3,TX+3], b in [3,TY+3]
                 int q = t - BP * BR;
                 int a = 3 + q % XP, b = 3 + q / XP;
@@ -588,22 +595,38 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
         // tile's north row / east column.
         auto flux_uu = [&](int a, int b) {      // ccc: F_uu and Lxx (advective_lorentz_flux_hBx_bx :38-60)
             double ut = sym4(RAW(s_u, a - 1, b), RAW(s_u, a, b), RAW(s_u, a + 1, b), RAW(s_u, a + 2, b));
+#if SWMHD_STRICT
             FXc(s_Fuu, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_u, a + 1, b), 1, ut, eps), RAW(s_h, a, b));
+#else
+            const double mom_ = fdiv(p.dy * upwind_weno(&RAW(s_u, a + 1, b), 1, ut, eps), RAW(s_h, a, b));
+#endif
             double ul = 0.5 * (Bf(s_hBx, a, b) + Bf(s_hBx, a + 1, b));
             double Lq = third(Bf(s_Bx, a + 1, b), Bf(s_Bx, a, b), Bf(s_Bx, a - 1, b));
             double Rq = thirdR(Bf(s_Bx, a + 2, b), Bf(s_Bx, a + 1, b), Bf(s_Bx, a, b));
+#if SWMHD_STRICT
             FXc(s_Lxx, a, b) = p.dy * upwind_sel(ul, Lq, Rq);
+#else
+            FXc(s_Fuu, a, b) = p.dy * upwind_sel(ul, Lq, Rq) - mom_;      // FAST: Lorentz minus momentum flux, one array
+#endif
         };
         auto flux_uv = [&](int a, int b) {      // ffc: F_uv and Lxy (advective_lorentz_flux_hBx_by :86-108)
             int gjf = p.gj0 + j0 + (b - 3);
             double u2 = sym2(RAW(s_u, a, b - 1), RAW(s_u, a, b));
             double u4 = sym4(RAW(s_u, a, b - 2), RAW(s_u, a, b - 1), RAW(s_u, a, b), RAW(s_u, a, b + 1));
             double ut = ybuf(by, gjf, 2, NyG) ? u2 : u4;
+#if SWMHD_STRICT
             FX3(s_Fuv, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_v, a, b), 1, ut, eps), HF(a, b));
+#else
+            const double mom_ = fdiv(p.dy * upwind_weno(&RAW(s_v, a, b), 1, ut, eps), HF(a, b));
+#endif
             double ul = 0.5 * (Bf(s_hBx, a, b - 1) + Bf(s_hBx, a, b));
             double Lq = third(Bf(s_By, a, b), Bf(s_By, a - 1, b), Bf(s_By, a - 2, b));
             double Rq = thirdR(Bf(s_By, a + 1, b), Bf(s_By, a, b), Bf(s_By, a - 1, b));
+#if SWMHD_STRICT
             FX3(s_Lxy, a, b) = p.dy * upwind_sel(ul, Lq, Rq);
+#else
+            FX3(s_Fuv, a, b) = p.dy * upwind_sel(ul, Lq, Rq) - mom_;      // FAST: Lorentz minus momentum flux, one array
+#endif
         };
         auto flux_tx = [&](int a, int b) {      // fcc: tracer transport flux and uh/ℑx h
             double vel = RAW(s_u, a, b), hx = Bf(s_hx, a, b);
@@ -611,15 +634,18 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             FX3(s_Tx, a, b) = fdiv(p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps), hx);
             FX3(s_uq, a, b) = fdiv(vel, hx);
 #else
-            double rhx = frcp(hx);
-            FX3(s_Tx, a, b) = (p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps)) * rhx;
-            FX3(s_uq, a, b) = vel * rhx;
+            FX3(s_Tx, a, b) = (p.dy * upwind_weno(&RAW(s_A, a, b), 1, vel, eps)) * hx;   // hx holds 1/ℑx h here
+            FX3(s_uq, a, b) = vel * hx;
 #endif
         };
         auto flux_vu = [&](int a, int b) {      // ffc: F_vu and Lyx (advective_lorentz_flux_hBy_bx :62-84 with edge branches)
             int gjf = p.gj0 + j0 + (b - 3);
             double vt = sym4(RAW(s_v, a - 2, b), RAW(s_v, a - 1, b), RAW(s_v, a, b), RAW(s_v, a + 1, b));
+#if SWMHD_STRICT
             FY3(s_Fvu, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_u, a, b), W, vt, eps, ybuf(by, gjf, 3, NyG)), HF(a, b));
+#else
+            const double mom_ = fdiv(p.dx * upwind_weno_buf(&RAW(s_u, a, b), W, vt, eps, ybuf(by, gjf, 3, NyG)), HF(a, b));
+#endif
             double vl = 0.5 * (Bf(s_hBy, a - 1, b) + Bf(s_hBy, a, b));
             double L3 = third(Bf(s_Bx, a, b), Bf(s_Bx, a, b - 1), Bf(s_Bx, a, b - 2));
             double R3 = thirdR(Bf(s_Bx, a, b + 1), Bf(s_Bx, a, b), Bf(s_Bx, a, b - 1));
@@ -629,14 +655,22 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
                 if (gjf == 1) { Lq = R1; Rq = R1; } else if (gjf == 2) { Lq = L1; Rq = R3; }
                 else if (gjf == NyG) { Lq = L3; Rq = R1; } else if (gjf == NyG + 1) { Lq = L1; Rq = L1; }
             }
+#if SWMHD_STRICT
             FY3(s_Lyx, a, b) = p.dx * upwind_sel(vl, Lq, Rq);
+#else
+            FY3(s_Fvu, a, b) = p.dx * upwind_sel(vl, Lq, Rq) - mom_;      // FAST: Lorentz minus momentum flux, one array
+#endif
         };
         auto flux_vv = [&](int a, int b) {      // ccc: F_vv and Lyy (advective_lorentz_flux_hBy_by :110-132)
             int gjc = p.gj0 + j0 + (b - 3);                         // global cell row
             double v2 = sym2(RAW(s_v, a, b), RAW(s_v, a, b + 1));
             double v4 = sym4(RAW(s_v, a, b - 1), RAW(s_v, a, b), RAW(s_v, a, b + 1), RAW(s_v, a, b + 2));
             double vt = ybuf(by, gjc + 1, 2, NyG + 1) ? v2 : v4;
+#if SWMHD_STRICT
             FYc(s_Fvv, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_v, a, b + 1), W, vt, eps, ybuf(by, gjc + 1, 3, NyG + 1)), RAW(s_h, a, b));
+#else
+            const double mom_ = fdiv(p.dx * upwind_weno_buf(&RAW(s_v, a, b + 1), W, vt, eps, ybuf(by, gjc + 1, 3, NyG + 1)), RAW(s_h, a, b));
+#endif
             double vl = 0.5 * (Bf(s_hBy, a, b) + Bf(s_hBy, a, b + 1));
             double L3 = third(Bf(s_By, a, b + 1), Bf(s_By, a, b), Bf(s_By, a, b - 1));
             double R3 = thirdR(Bf(s_By, a, b + 2), Bf(s_By, a, b + 1), Bf(s_By, a, b));
@@ -646,7 +680,11 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
                 if (gjc == 0) { Lq = R1; Rq = R1; } else if (gjc == 1) { Lq = L1; Rq = R3; }
                 else if (gjc == NyG - 1) { Lq = L3; Rq = R1; } else if (gjc == NyG) { Lq = L1; Rq = L1; }
             }
+#if SWMHD_STRICT
             FYc(s_Lyy, a, b) = p.dx * upwind_sel(vl, Lq, Rq);
+#else
+            FYc(s_Fvv, a, b) = p.dx * upwind_sel(vl, Lq, Rq) - mom_;      // FAST: Lorentz minus momentum flux, one array
+#endif
         };
         auto flux_ty = [&](int a, int b) {      // cfc: tracer transport flux and vh/ℑy h
             int gjf = p.gj0 + j0 + (b - 3);
@@ -655,9 +693,8 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             FY3(s_Ty, a, b) = fdiv(p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG)), hy);
             FY3(s_vq, a, b) = fdiv(vel, hy);
 #else
-            double rhy = frcp(hy);
-            FY3(s_Ty, a, b) = (p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG))) * rhy;
-            FY3(s_vq, a, b) = vel * rhy;
+            FY3(s_Ty, a, b) = (p.dx * upwind_weno_buf(&RAW(s_A, a, b), W, vel, eps, ybuf(by, gjf, 3, NyG))) * hy;   // 1/ℑy h
+            FY3(s_vq, a, b) = vel * hy;
 #endif
         };
         flux_uu(li - 1, lj); flux_uv(li, lj); flux_tx(li, lj);
@@ -672,12 +709,20 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             for (int q = tid; q < NDG; q += NT) {
                 if (q < YP * YR) {
                     int a = 3 + q % YP, b = 3 + q / YP;
+#if SWMHD_STRICT
                     double bx = fdiv(-DIVDY(RAW(s_A, a, b) - RAW(s_A, a, b - 1)), Bf(s_hy, a, b));
+#else
+                    double bx = -DIVDY(RAW(s_A, a, b) - RAW(s_A, a, b - 1)) * Bf(s_hy, a, b);
+#endif
                     s_sqBx[q] = bx * bx;
                 } else {
                     int r = q - YP * YR;
                     int a = 3 + r % XP, b = 2 + r / XP;
+#if SWMHD_STRICT
                     double by_ = fdiv(DIVDX(RAW(s_A, a, b) - RAW(s_A, a - 1, b)), Bf(s_hx, a, b));
+#else
+                    double by_ = DIVDX(RAW(s_A, a, b) - RAW(s_A, a - 1, b)) * Bf(s_hx, a, b);
+#endif
                     s_sqBy[r] = by_ * by_;
                 }
             }
@@ -696,15 +741,23 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
                 double dm = p.inv_az * ((FXc(s_Fuu, li, lj) - FXc(s_Fuu, li - 1, lj)) + (FY3(s_Fvu, li, lj + 1) - FY3(s_Fvu, li, lj)));
                 double pg = DIVDX(__dsub_rn(Pc, Pw));
                 double vhat = avg4(RAW(s_v, li - 1, lj), RAW(s_v, li, lj), RAW(s_v, li - 1, lj + 1), RAW(s_v, li, lj + 1));
+#if SWMHD_STRICT
                 double lor = p.inv_az * ((FXc(s_Lxx, li, lj) - FXc(s_Lxx, li - 1, lj)) + (FY3(s_Lyx, li, lj + 1) - FY3(s_Lyx, li, lj)));
                 Gn0 = ((-dm - pg) + p.f * vhat) + lor;
+#else
+                Gn0 = fma(p.f, vhat, dm - pg);                      // dm already holds div(Lorentz - momentum flux)
+#endif
             }
             if (!(p.by && gj < 2)) {   // Gvh
                 double dm = p.inv_az * ((FX3(s_Fuv, li + 1, lj) - FX3(s_Fuv, li, lj)) + (FYc(s_Fvv, li, lj) - FYc(s_Fvv, li, lj - 1)));
                 double pg = DIVDY(__dsub_rn(Pc, Ps));
                 double uhat = avg4(RAW(s_u, li, lj - 1), RAW(s_u, li + 1, lj - 1), RAW(s_u, li, lj), RAW(s_u, li + 1, lj));
+#if SWMHD_STRICT
                 double lor = p.inv_az * ((FX3(s_Lxy, li + 1, lj) - FX3(s_Lxy, li, lj)) + (FYc(s_Lyy, li, lj) - FYc(s_Lyy, li, lj - 1)));
                 Gn1 = ((-dm - pg) - p.f * uhat) + lor;
+#else
+                Gn1 = fma(-p.f, uhat, dm - pg);
+#endif
             }
             {   // Gh (centred), GA
 #if SWMHD_STRICT
