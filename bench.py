@@ -123,12 +123,13 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(form):
-    """DRAM bytes per substage-kernel launch from the committed ncu --set full capture, or None."""
+def ncu_traffic(form, ncells):
+    """DRAM bytes per substage-kernel launch (mean of the three stages) from the committed
+    ncu --set full capture (profiles/traffic.json holds bytes per cell measured at 2048^2), or None."""
     p = ROOT / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(form)
+            return json.loads(p.read_text())[form]["bytes_per_cell_per_launch_mean"] * ncells
         except Exception:
             return None
     return None
@@ -245,7 +246,7 @@ def run_native(args):
         mean_bytes = ncell * sum(STAGE_BYTES) / 3.0
         mean_ms = sum(st_ms) / 3.0
         achieved = mean_bytes / (mean_ms * 1e-3) / 1e9
-        traffic = ncu_traffic(args.form)
+        traffic = ncu_traffic(args.form, ncell)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": "swmhd::substage_kernel<FORM,STAGE>",
                 "bytes_per_launch": mean_bytes, "ms_per_launch": mean_ms,
