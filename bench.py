@@ -50,14 +50,16 @@ def parse():
     ap.add_argument("--form", default="jacobian", choices=["jacobian", "divergence"])
     ap.add_argument("--arith", default="fast", choices=["fast", "strict"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--topology", default="periodic", choices=["periodic", "bounded"], help="y topology (x is periodic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------
-def initial_state(grid, form, pinned=False):
-    """IC-J (SWMHD_example.jl:36-40) or IC-D (divergence_sw_mhd.jl:33-38) on the host."""
+def initial_state(grid, form, pinned=False, bounded=False):
+    """IC-J (SWMHD_example.jl:36-40) or IC-D (divergence_sw_mhd.jl:33-38) on the host; Bounded-y:
+    IC-B, A = -0.05 y with its gradient BC and a unit vortex (divergence_sw_mhd.jl:17,34-37)."""
     from swmhd_b200 import abi
     U = []
     for k in range(4):
@@ -69,7 +71,11 @@ def initial_state(grid, form, pinned=False):
             a = np.zeros(shape)
         U.append(a)
     grid.set_interior(U[abi.H], abi.H, 1.0)
-    if form == abi.JACOBIAN:
+    if bounded:
+        grid.set_interior(U[abi.U], abi.U, lambda x, y, z: y * np.exp(-(x ** 2 + y ** 2)))
+        grid.set_interior(U[abi.V], abi.V, lambda x, y, z: -x * np.exp(-(x ** 2 + y ** 2)))
+        grid.set_interior(U[abi.A], abi.A, lambda x, y, z: -0.05 * y)
+    elif form == abi.JACOBIAN:
         grid.set_interior(U[abi.U], abi.U, lambda x, y, z: 5 * y * np.exp(-(x ** 2 + y ** 2)))
         grid.set_interior(U[abi.V], abi.V, lambda x, y, z: -5 * x * np.exp(-(x ** 2 + y ** 2)))
         grid.set_interior(U[abi.A], abi.A, lambda x, y, z: 0.5 * np.abs(y))
@@ -213,13 +219,17 @@ def run_native(args):
     K, W = args.steps, args.warmup
     sampler = ClockSampler(local) if rank == 0 else None
 
-    cfg_g = abi.make_config(Nx, NyG, Lx=Lx, Ly=Ly, formulation=form, arith=arith, device=local)
+    bounded = args.topology == "bounded"
+    from swmhd_b200.grids import Periodic, Bounded, Flat
+    topo = (Periodic, Bounded if bounded else Periodic, Flat)
+    cfg_g = abi.make_config(Nx, NyG, Lx=Lx, Ly=Ly, formulation=form, arith=arith, device=local,
+                            topo_y=abi.BOUNDED if bounded else abi.PERIODIC, A_gradient=(-0.05, -0.05) if bounded else None)
     e2e = None
     roof = None
     launches = 0
     if world == 1:
-        grid = RectilinearGrid((Nx, NyG), (-Lx / 2, Lx / 2), (-Ly / 2, Ly / 2))
-        U0 = initial_state(grid, form, pinned=True)
+        grid = RectilinearGrid((Nx, NyG), (-Lx / 2, Lx / 2), (-Ly / 2, Ly / 2), topology=topo)
+        U0 = initial_state(grid, form, pinned=True, bounded=bounded)
         ctx = Context(cfg_g)
         ctx.set_state(U0)
         ctx.fill_halos()
@@ -254,7 +264,7 @@ def run_native(args):
                 "second_ceiling": "FP64 issue: 148 SM x 64 lanes; see DESIGN.md (the kernel is FP64-pipe bound, not HBM bound)"}
         finite = all(d["all_finite"] for d in diags)
         # ---- end to end through the public API with host buffers -------------------------
-        if not args.no_e2e:
+        if not args.no_e2e and not bounded:
             from swmhd_b200 import models as M
             ctx.close()
             mgrid = M.RectilinearGrid(size=(Nx, NyG), x=(-Lx / 2, Lx / 2), y=(-Ly / 2, Ly / 2), topology=(M.Periodic, M.Periodic, M.Flat))
@@ -289,12 +299,13 @@ def run_native(args):
             model.close()
         else:
             ctx.close()
+            e2e = None
     else:
         from swmhd_b200.distributed import SlabModel, split_rows
         j0, ny = split_rows(NyG, world)[rank]
         # slab ICs straight from the closed forms at this slab's nodes (halo rows come from the exchange)
-        gridl = RectilinearGrid((Nx, ny), (-Lx / 2, Lx / 2), (-Ly / 2 + j0 * (Ly / NyG), -Ly / 2 + (j0 + ny) * (Ly / NyG)))
-        U0 = initial_state(gridl, form, pinned=True)
+        gridl = RectilinearGrid((Nx, ny), (-Lx / 2, Lx / 2), (-Ly / 2 + j0 * (Ly / NyG), -Ly / 2 + (j0 + ny) * (Ly / NyG)), topology=topo)
+        U0 = initial_state(gridl, form, pinned=True, bounded=bounded)
         sm = SlabModel(cfg_g, rank, world, local)
         sm.set_state(U0)
         sm.fill_halos()
@@ -356,9 +367,9 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.form} formulation {Nx}x{NyG} periodic FP64 RK3 step, energy/div(hB) diagnostics every step "
+        "config": {"workload": f"{args.form} formulation {Nx}x{NyG} {'Bounded-y' if bounded else 'periodic'} FP64 RK3 step, energy/div(hB) diagnostics every step "
                                f"(BASELINE config 3 per GPU; y-slabs of {Nx}x{NyG // world})",
-                   "arith": args.arith, "dt": dt, "ic": "IC-J (SWMHD_example.jl:36-40)" if form == abi.JACOBIAN else "IC-D (divergence_sw_mhd.jl:33-38)",
+                   "arith": args.arith, "dt": dt, "ic": "IC-B (divergence_sw_mhd.jl:17,34-37)" if bounded else ("IC-J (SWMHD_example.jl:36-40)" if form == abi.JACOBIAN else "IC-D (divergence_sw_mhd.jl:33-38)"),
                    "l2": "working set 12 fields x %.0f MB >> 126 MB L2 (inputs larger than L2, no flush needed)" % (Nx * (NyG // world) * 8 / 1e6),
                    "timing": "CUDA events on the launching stream around K steps, max over ranks",
                    "all_finite": bool(finite)},

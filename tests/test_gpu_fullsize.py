@@ -1,0 +1,108 @@
+"""BASELINE.json configurations at their full sizes on the GPU.
+
+Config 2 (divergence 1024^2) and the Jacobian form at 1024^2 are compared with the CPU oracle directly
+(one step costs the oracle about a second).  At 4096^2 the oracle is too slow for a test, so the CUDA
+path is checked through size-independent properties: strict == fast within tolerance, mass
+conservation, div(hB) at round-off, constant-A invariance, batching invariance and the point symmetry
+of the initial-value problem.  The published energy traces are reproduced by the CUDA path as well."""
+import numpy as np
+import pytest
+
+from swmhd_b200 import abi
+from swmhd_b200.context import Context
+from oracle import pyoracle as O
+from cases import make_case, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu_run(cfg, U, dt, nsteps, diag=False):
+    ctx = Context(cfg)
+    ctx.set_state(U)
+    ctx.fill_halos()
+    tr = ctx.step_diag(dt, nsteps) if diag else ctx.step(dt, nsteps)
+    out = ctx.get_state()
+    d = ctx.diagnostics()
+    ctx.close()
+    return out, d, tr
+
+
+@pytest.mark.parametrize("kind", ["D", "J"])
+def test_1024_one_and_ten_steps_vs_oracle(kind):
+    """BASELINE config 2: divergence_sw_mhd.jl at 1024^2 periodic FP64, validated against the CPU run."""
+    N, dt = 1024, 0.01 * 64 / 1024
+    g, cfg, U = make_case(kind, N, arith=abi.ARITH_STRICT)
+    Us, _, _ = gpu_run(cfg, U, dt, 1)
+    cfg_f = abi.Config.from_buffer_copy(cfg)
+    cfg_f.arith = abi.ARITH_FAST
+    Uf1, _, _ = gpu_run(cfg_f, U, dt, 1)
+    Uf10, _, _ = gpu_run(cfg_f, U, dt, 10)
+    O.fill_halos(cfg, U)
+    O.step(cfg, U, dt, 1)
+    for k in range(4):
+        assert np.array_equal(Us[k], U[k]), f"strict field {k}"
+        assert rel_l2(g, Uf1[k], U[k], k) <= 1e-12, f"fast field {k}"
+    O.step(cfg, U, dt, 9)
+    for k in range(4):
+        assert rel_l2(g, Uf10[k], U[k], k) <= 1e-11, f"fast 10 steps field {k}"
+
+
+@pytest.mark.parametrize("kind", ["J", "D"])
+def test_4096_properties(kind):
+    N, dt, nst = 4096, 0.01 * 64 / 4096, 6
+    g, cfg, U = make_case(kind, N, arith=abi.ARITH_FAST)
+    Uf, df, tr = gpu_run(cfg, U, dt, nst, diag=True)
+    cfg_s = abi.Config.from_buffer_copy(cfg)
+    cfg_s.arith = abi.ARITH_STRICT
+    Us, ds, _ = gpu_run(cfg_s, U, dt, nst)
+    for k in range(4):                                   # the two arithmetic modes agree to the stated tolerance
+        assert rel_l2(g, Uf[k], Us[k], k) <= 5e-12, k
+    m0 = float(N) * N                                    # h = 1 initially
+    assert abs(df["sum_h"] - m0) <= 2e-12 * m0           # flux form: mass conserved to round-off
+    assert df["max_abs_div_hB"] < 1e-11                  # div(hB) = 0 identically for hB = z x grad A
+    assert df["all_finite"] == 1 and df["min_h"] > 0.5
+    assert abs(tr[0]["pe"]) == 0.0 and (kind == "D" and tr[0]["ke"] == 0.0 or kind == "J")
+    e = [t["total"] for t in tr]
+    assert max(abs(x - e[0]) for x in e) <= 2e-5 * max(1.0, abs(e[0]))      # energy drift over 6 tiny steps (WENO dissipation at the |y| kink of IC-J)
+    # point symmetry of the IVP: (x,y) -> (-x,-y) maps u -> -u, v -> -v, h -> h, A -> A for IC-J;
+    # cell-centred fields of the periodic grid map i -> N+1-i, j -> N+1-j
+    h = g.interior(Uf[abi.H], abi.H)
+    assert np.abs(h - h[::-1, ::-1]).max() <= 1e-12
+    # batching invariance: 6 steps in one call == 2 + 4
+    ctx = Context(cfg)
+    ctx.set_state(U); ctx.fill_halos(); ctx.step(dt, 2); ctx.step(dt, 4)
+    Ub = ctx.get_state(); ctx.close()
+    for k in range(4):
+        assert np.array_equal(Ub[k], Uf[k])
+
+
+def test_constant_A_stays_constant_4096():
+    g, cfg, U = make_case("J", 4096, arith=abi.ARITH_FAST)
+    U[abi.A][...] = 0.75
+    out, d, _ = gpu_run(cfg, U, 0.01 * 64 / 4096, 4)
+    assert np.abs(g.interior(out[abi.A], abi.A) - 0.75).max() < 1e-13
+    assert abs(d["me"]) < 1e-20
+
+
+TRACE_T = [5, 10, 15, 20, 25, 30]
+TRACES = {
+    "G": dict(ke=[.00053, .00146, .00212, .00246, .00262, .00274], me=[.02116, .02022, .01955, .01921, .01904, .01887]),
+    "GD": dict(ke=[.00054, .00148, .00214, .00250, .00268, .00282], me=[.02116, .02021, .01955, .01922, .01905, .01891]),
+}
+
+
+@pytest.mark.parametrize("kind", ["G", "GD"])
+def test_published_energy_traces_on_gpu(kind):
+    """energy_plots/*/64x64_two_Gaussians_low_B.png (digitised) from the CUDA path: 3000 RK3 steps."""
+    g, cfg, U = make_case(kind, 64, arith=abi.ARITH_FAST)
+    ctx = Context(cfg)
+    ctx.set_state(U)
+    ctx.fill_halos()
+    t = 0
+    for T, ke, me in zip(TRACE_T, TRACES[kind]["ke"], TRACES[kind]["me"]):
+        ctx.step(0.01, (T - t) * 100)
+        t = T
+        d = ctx.diagnostics()
+        assert abs(d["ke"] - ke) <= 2.5e-5 and abs(d["me"] - me) <= 2.5e-5, (T, d["ke"], ke, d["me"], me)
+    assert abs(ctx.time - 30.0) < 1e-9 and ctx.iteration == 3000
+    ctx.close()
