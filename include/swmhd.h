@@ -143,6 +143,12 @@ int  swmhd_tendencies(swmhd_ctx *ctx, double *const G_host[4], size_t n_each);
    SWMHD_example.jl:47-63,67-77; divergence_sw_mhd.jl:42-59,63-75 */
 int  swmhd_diagnostics(swmhd_ctx *ctx, swmhd_diag *out);
 
+/* The field writer's outputs (SWMHD_example.jl:67-69,81-84; divergence_sw_mhd.jl:63-66,77-82) computed on
+   the device: u, v (velocities; uh/Ix(h), vh/Iy(h) for DIVERGENCE) and s = sqrt(u^2 + v^2) at (Face, Center),
+   as parent arrays of u-, v- and u-shaped fields (halos filled).  A is swmhd_get_field(ctx, SWMHD_A).
+   Call between steps only (it stages through the tendency buffers). */
+int  swmhd_get_outputs(swmhd_ctx *ctx, double *u_host, double *v_host, double *s_host);
+
 /* model.clock: time and iteration as advanced by the RK3 stages */
 double  swmhd_time(const swmhd_ctx *ctx);
 int64_t swmhd_iteration(const swmhd_ctx *ctx);

@@ -92,6 +92,7 @@ SYMBOLS = [
     ("swmhd_substage", C.c_int, [_ctx, C.c_double, C.c_int]),
     ("swmhd_tendencies", C.c_int, [_ctx, C.POINTER(_dp), C.c_size_t]),
     ("swmhd_diagnostics", C.c_int, [_ctx, C.POINTER(Diag)]),
+    ("swmhd_get_outputs", C.c_int, [_ctx, _dp, _dp, _dp]),
     ("swmhd_time", C.c_double, [_ctx]),
     ("swmhd_iteration", C.c_int64, [_ctx]),
     ("swmhd_set_clock", C.c_int, [_ctx, C.c_double, C.c_int64]),

@@ -110,6 +110,12 @@ class Context:
         self._ck(rc)
         return d.as_dict()
 
+    def get_outputs(self):
+        """(u, v, s) parent arrays of the field writer, computed on the device."""
+        u, v, s = self.new_parent(abi.U), self.new_parent(abi.V), self.new_parent(abi.U)
+        self._ck(self.lib.swmhd_get_outputs(self._h, _ptr(u), _ptr(v), _ptr(s)))
+        return u, v, s
+
     # -- clock ------------------------------------------------------------------------------
     @property
     def time(self):

@@ -182,7 +182,36 @@ __global__ void __launch_bounds__(FT) diag_final_kernel(const double *partials, 
     if (threadIdx.x == 0) g_final_ticket = 0;
 }
 
+// ---------------------------------------------------------------------------
+// Output quantities of the reference's field writer (SWMHD_example.jl:67-69,81-84;
+// divergence_sw_mhd.jl:63-66,77-82): u, v (velocities: uh/ℑx h, vh/ℑy h for the conservative form)
+// and the speed s = sqrt(u^2 + ℑxyᶠᶜᵃ(v^2)) at (Face, Center) — AbstractOperations interpolates the
+// second operand to the location of the first.  One thread per cell of the region
+// [0, Nx+2] x [0, Ny+2]; the caller fills the remaining halo cells with the halo kernel.
+__global__ void output_kernel(OutputParams p) {
+    const int P = p.P;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // logical i in [0, Nx+2]
+    const int j = blockIdx.y;                                     // logical j in [0, Ny+2]
+    if (i > p.Nx + 2 || j > p.Ny + 2) return;
+    auto ix = [&](int a, int b) { return (size_t)(a + 2) + (size_t)P * (size_t)(b + 2); };
+    const double *U = p.U[0], *V = p.U[1], *H = p.U[2];
+    auto uvel = [&](int a, int b) { return p.form == 0 ? U[ix(a, b)] : U[ix(a, b)] / (0.5 * (H[ix(a - 1, b)] + H[ix(a, b)])); };
+    auto vvel = [&](int a, int b) { return p.form == 0 ? V[ix(a, b)] : V[ix(a, b)] / (0.5 * (H[ix(a, b - 1)] + H[ix(a, b)])); };
+    const double u = uvel(i, j), v = vvel(i, j);
+    auto sq = [](double x) { return x * x; };
+    const double v2 = 0.5 * (0.5 * (sq(vvel(i - 1, j)) + sq(v)) + 0.5 * (sq(vvel(i - 1, j + 1)) + sq(vvel(i, j + 1))));
+    p.out_u[ix(i, j)] = u;
+    p.out_v[ix(i, j)] = v;
+    p.out_s[ix(i, j)] = sqrt(sq(u) + v2);
+}
+
 } // namespace
+
+cudaError_t launch_output(const OutputParams &p, cudaStream_t st) {
+    dim3 grid((p.Nx + 3 + 127) / 128, p.Ny + 3);
+    output_kernel<<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_halo(const HaloParams &p, cudaStream_t st) {
     int nrow = p.j_hi - p.j_lo + 1;

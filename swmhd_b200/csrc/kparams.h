@@ -50,6 +50,12 @@ struct DiagParams {
     int nblocks;
 };
 
+struct OutputParams {
+    int Nx, Ny, P, form;
+    const double *U[4];
+    double *out_u, *out_v, *out_s;
+};
+
 constexpr int NDIAG = 9; // sums: ke, me, pe, sum_h [0..3]; maxima: |u|, |A|, -h, |div hB| [4..7]; nonfinite count [8]
 
 // kernel launchers (one strict + one fast instantiation of substage_kernel.cu)
@@ -61,5 +67,6 @@ cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st);
 cudaError_t launch_diag_final(const double *partials, int nblocks, double *stage, double *out9, cudaStream_t st);
 int diag_stage_doubles();
 int diag_blocks(int Nx, int Ny);
+cudaError_t launch_output(const OutputParams &p, cudaStream_t st);
 
 } // namespace swmhd

@@ -427,6 +427,34 @@ extern "C" int swmhd_tendencies(swmhd_ctx *ctx, double *const G_host[4], size_t 
     return SWMHD_OK;
 }
 
+// u, v, s of the field writer, computed on the device from the current state.  The three results are
+// staged in the tendency buffers G[0..2] (free between steps: stage 1 never reads G^-), halos filled
+// like u-, v- and u-located fields, then copied to the host parent arrays.
+extern "C" int swmhd_get_outputs(swmhd_ctx *ctx, double *u_host, double *v_host, double *s_host) {
+    if (!ctx || !u_host || !v_host || !s_host) return SWMHD_ERR_ARG;
+    if (ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "outputs can only be taken between steps");
+    CK(cudaSetDevice(ctx->cfg.device));
+    OutputParams o;
+    o.Nx = ctx->Nx; o.Ny = ctx->Ny; o.P = ctx->P; o.form = ctx->cfg.formulation;
+    for (int k = 0; k < 4; k++) o.U[k] = ctx->U[ctx->cur][k];
+    o.out_u = ctx->G[0]; o.out_v = ctx->G[1]; o.out_s = ctx->G[2];
+    ctx->launches++;
+    CK(launch_output(o, ctx->main));
+    if (ctx->cfg.world == 1) {          // periodic / wall halos of the outputs: (u, v, s) behave like (u, v, u)
+        double *outs[4] = {ctx->G[0], ctx->G[1], ctx->G[2], ctx->G[2]};
+        HaloParams h = halo_params(ctx, outs, 3, ctx->Ny + 2, true);
+        h.grad = 0;
+        h.rows[2] = ctx->rows[0]; h.rows[3] = ctx->rows[0];
+        ctx->launches++;
+        CK(launch_halo(h, ctx->main));
+    }
+    CK(cudaMemcpyAsync(u_host, ctx->G[0], ctx->len[0] * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    CK(cudaMemcpyAsync(v_host, ctx->G[1], ctx->len[1] * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    CK(cudaMemcpyAsync(s_host, ctx->G[2], ctx->len[0] * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+    CK(cudaStreamSynchronize(ctx->main));
+    return SWMHD_OK;
+}
+
 extern "C" double swmhd_time(const swmhd_ctx *ctx) { return ctx ? ctx->time : NAN; }
 extern "C" int64_t swmhd_iteration(const swmhd_ctx *ctx) { return ctx ? ctx->iter : -1; }
 extern "C" int swmhd_set_clock(swmhd_ctx *ctx, double time, int64_t iteration) {

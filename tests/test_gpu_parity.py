@@ -193,3 +193,38 @@ def test_bounded_y_matches_oracle(kind, arith):
             assert np.array_equal(Ug[k], U[k]), (k, np.abs(Ug[k] - U[k]).max())
         else:
             assert rel_l2(g, Ug[k], U[k], k) <= 5e-12, k
+
+
+@pytest.mark.parametrize("kind", ["J", "D"])
+def test_device_side_writer_outputs(kind):
+    """swmhd_get_outputs: u, v, s = sqrt(u^2 + v^2) of the reference's field writer
+    (SWMHD_example.jl:67-69,81-84; divergence_sw_mhd.jl:63-66) vs a numpy restatement."""
+    g, cfg, U = make_case(kind, 72, Ny=48, perturb=23)
+    ctx = Context(cfg)
+    ctx.set_state(U)
+    ctx.fill_halos()
+    ctx.step(0.004, 2)
+    St = ctx.get_state()
+    u_o, v_o, s_o = ctx.get_outputs()
+    St2 = ctx.get_state()
+    ctx.step(0.004, 1)                      # the staging buffers are free again: stepping still works
+    ctx.close()
+    for k in range(4):
+        assert np.array_equal(St[k], St2[k])
+    u, v, h = St[0], St[1], St[2]
+    if kind == "D":
+        uvel = u / (0.5 * (np.roll(h, 1, axis=1) + h))
+        vvel = v / (0.5 * (np.roll(h, 1, axis=0) + h))
+    else:
+        uvel, vvel = u, v
+    v2 = vvel ** 2
+    ixf = 0.5 * (np.roll(v2, 1, axis=1) + v2)
+    ixy = 0.5 * (ixf + np.roll(ixf, -1, axis=0))
+    s = np.sqrt(uvel ** 2 + ixy)
+    it = (slice(3, 3 + g.Ny), slice(3, 3 + g.Nx))
+    assert np.allclose(u_o[it], uvel[it], rtol=1e-14, atol=0)
+    assert np.allclose(v_o[it], vvel[it], rtol=1e-14, atol=0)
+    assert np.allclose(s_o[it], s[it], rtol=1e-14, atol=1e-300)
+    # halos of the outputs are the periodic images of their interiors (with_halos = true writers)
+    assert np.array_equal(s_o[it][:, :3], s_o[3:3 + g.Ny, 3 + g.Nx:6 + g.Nx])
+    assert np.array_equal(s_o[it][:3, :], s_o[3 + g.Ny:6 + g.Ny, 3:3 + g.Nx])
