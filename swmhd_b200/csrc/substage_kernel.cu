@@ -63,6 +63,8 @@ __device__ __forceinline__ double fdiv(double a, double b) { return a / b; }
 #define DIVDX(x) ((x) / p.dx)
 #define DIVDY(x) ((x) / p.dy)
 #define DIVAZ(x) ((x) / (p.dx * p.dy))
+#define FXS p.dy
+#define FYS p.dx
 #else
 __device__ __forceinline__ double frcp(double x) {
     double r;
@@ -77,6 +79,8 @@ __device__ __forceinline__ double fdiv(double a, double b) { return a * frcp(b);
 #define DIVDX(x) ((x) * p.rdx)
 #define DIVDY(x) ((x) * p.rdy)
 #define DIVAZ(x) ((x) * p.inv_az)
+#define FXS 1.0
+#define FYS 1.0
 #endif
 
 // ---- WENO5-Z.  a..e = psi[f-3..f+1] in upwind ("left") orientation ------------
@@ -128,14 +132,16 @@ struct WenoDiff { double c, d1, d2, d3, d4; };
 __device__ __forceinline__ WenoDiff weno_diffs(double a, double b, double c, double d, double e) {
     WenoDiff w; w.c = c; w.d1 = b - a; w.d2 = c - b; w.d3 = d - c; w.d4 = e - d; return w;
 }
-// acc_k += k13 * D_k^2 + k14 * E_k^2   (k13 = 13/12 s, k14 = 1/4 s)
-__device__ __forceinline__ void weno_beta_acc(const WenoDiff &w, double k13, double k14, double &c0, double &c1, double &c2) {
+// acc_k += D_k^2 + r E_k^2 with r = (1/4)/(13/12) = 3/13: the smoothness indicators divided by 13/12.
+// The Z weights depend only on ratios tau/c_k, so a common scale of (beta_k + eps) is free: eps is scaled too.
+__device__ __forceinline__ void weno_beta_acc(const WenoDiff &w, double &c0, double &c1, double &c2) {
+    constexpr double r = 3.0 / 13.0;
     const double D0 = w.d4 - w.d3, E0 = fma(-3.0, w.d3, w.d4);      // (c,d,e): c-2d+e, 3c-4d+e
     const double D1 = w.d3 - w.d2, E1 = w.d2 + w.d3;               // (b,c,d): b-2c+d, -(b-d)
     const double D2 = w.d2 - w.d1, E2 = fma(3.0, w.d2, -w.d1);     // (a,b,c): a-2b+c, a-4b+3c
-    c0 = fma(k13 * D0, D0, fma(k14 * E0, E0, c0));
-    c1 = fma(k13 * D1, D1, fma(k14 * E1, E1, c1));
-    c2 = fma(k13 * D2, D2, fma(k14 * E2, E2, c2));
+    c0 = fma(D0, D0, fma(r * E0, E0, c0));
+    c1 = fma(D1, D1, fma(r * E1, E1, c1));
+    c2 = fma(D2, D2, fma(r * E2, E2, c2));
 }
 __device__ __forceinline__ double weno_blend_c(const WenoDiff &w, double c0, double c1, double c2) {
     const double tau = c2 - c0, t2 = tau * tau;
@@ -151,14 +157,16 @@ __device__ __forceinline__ double weno_blend_c(const WenoDiff &w, double c0, dou
 }
 __device__ __forceinline__ double weno5(double a, double b, double c, double d, double e, double eps) {
     const WenoDiff w = weno_diffs(a, b, c, d, e);
-    double c0 = eps, c1 = eps, c2 = eps;
-    weno_beta_acc(w, 13.0 / 12.0, 0.25, c0, c1, c2);
+    const double es = eps * (12.0 / 13.0);
+    double c0 = es, c1 = es, c2 = es;
+    weno_beta_acc(w, c0, c1, c2);
     return weno_blend_c(w, c0, c1, c2);
 }
 __device__ __forceinline__ double weno5_vs(const double *qz, const double *qu, const double *qv, int s, double eps) {
-    double c0 = eps, c1 = eps, c2 = eps;
-    weno_beta_acc(weno_diffs(qu[0], qu[s], qu[2 * s], qu[3 * s], qu[4 * s]), 13.0 / 24.0, 0.125, c0, c1, c2);
-    weno_beta_acc(weno_diffs(qv[0], qv[s], qv[2 * s], qv[3 * s], qv[4 * s]), 13.0 / 24.0, 0.125, c0, c1, c2);
+    const double es = eps * (24.0 / 13.0);      // beta = (beta_u + beta_v)/2: common scale 13/24
+    double c0 = es, c1 = es, c2 = es;
+    weno_beta_acc(weno_diffs(qu[0], qu[s], qu[2 * s], qu[3 * s], qu[4 * s]), c0, c1, c2);
+    weno_beta_acc(weno_diffs(qv[0], qv[s], qv[2 * s], qv[3 * s], qv[4 * s]), c0, c1, c2);
     return weno_blend_c(weno_diffs(qz[0], qz[s], qz[2 * s], qz[3 * s], qz[4 * s]), c0, c1, c2);
 }
 #endif
@@ -384,40 +392,45 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
 #define FY(arr, a, b) arr[((b) - 3) * YP + (a) - 3]
 
         // ---- A: light derived fields (zeta, velocity-stencil averages, K, Bx, By [, diag B^2]) ----
-        constexpr int NXF = XP * XR, NYF = YP * YR, NZ = ZP * ZR, NC = CP * CR;
+        constexpr int NZ = ZP * ZR, NC = CP * CR;
         constexpr int NDG = DIAG ? NDG_ : 0;
-        for (int t = tid + NXF + NYF; t < NXF + NYF + NZ + NC + NDG; t += NT) {
-            if (t < NXF + NYF + NZ) {                               // zeta, ℑy u, ℑx v at ffc
-                int q = t - NXF - NYF;
-                int a = 1 + q % ZP, b = 1 + q / ZP;
-                double vc = RAW(s_v, a, b), vw = RAW(s_v, a - 1, b), uc = RAW(s_u, a, b), us = RAW(s_u, a, b - 1);
+        auto task_zeta = [&](int q) {                               // zeta, ℑy u, ℑx v at ffc
+            int a = 1 + q % ZP, b = 1 + q / ZP;
+            double vc = RAW(s_v, a, b), vw = RAW(s_v, a - 1, b), uc = RAW(s_u, a, b), us = RAW(s_u, a, b - 1);
 #if SWMHD_STRICT
-                Zf(s_z, a, b) = DIVAZ((p.dy * vc - p.dy * vw) - (p.dx * uc - p.dx * us));
+            Zf(s_z, a, b) = DIVAZ((p.dy * vc - p.dy * vw) - (p.dx * uc - p.dx * us));
 #else
-                Zf(s_z, a, b) = fma(vc - vw, p.rdx, (us - uc) * p.rdy);
+            Zf(s_z, a, b) = fma(vc - vw, p.rdx, (us - uc) * p.rdy);
 #endif
-                Zf(s_ut, a, b) = 0.5 * (us + uc);
-                Zf(s_vt, a, b) = 0.5 * (vw + vc);
-            } else if (t < NXF + NYF + NZ + NC) {                   // K, Bx, By at ccc
-                int q = t - NXF - NYF - NZ;
-                int a = 2 + q % CP, b = 2 + q / CP;
-                double u0 = RAW(s_u, a, b), u1 = RAW(s_u, a + 1, b), v0 = RAW(s_v, a, b), v1 = RAW(s_v, a, b + 1);
-                double hc = RAW(s_h, a, b);
+            Zf(s_ut, a, b) = 0.5 * (us + uc);
+            Zf(s_vt, a, b) = 0.5 * (vw + vc);
+        };
+        auto task_ccc = [&](int q) {                                // K, Bx, By at ccc
+            int a = 2 + q % CP, b = 2 + q / CP;
+            double u0 = RAW(s_u, a, b), u1 = RAW(s_u, a + 1, b), v0 = RAW(s_v, a, b), v1 = RAW(s_v, a, b + 1);
+            double hc = RAW(s_h, a, b);
 #if SWMHD_STRICT
-                Cc(s_K, a, b) = (0.5 * (u0 * u0 + u1 * u1) + 0.5 * (v0 * v0 + v1 * v1)) / 2.0;
-                double Ac = RAW(s_A, a, b);
-                double dyA0 = DIVDY(Ac - RAW(s_A, a, b - 1)), dyA1 = DIVDY(RAW(s_A, a, b + 1) - Ac);
-                double dxA0 = DIVDX(Ac - RAW(s_A, a - 1, b)), dxA1 = DIVDX(RAW(s_A, a + 1, b) - Ac);
-                Cc(s_Bx, a, b) = -(0.5 * (dyA0 + dyA1)) / hc;       // sw_mhd_jacobian_functions.jl:5-7
-                Cc(s_By, a, b) = (0.5 * (dxA0 + dxA1)) / hc;        // :1-3
+            Cc(s_K, a, b) = (0.5 * (u0 * u0 + u1 * u1) + 0.5 * (v0 * v0 + v1 * v1)) / 2.0;
+            double Ac = RAW(s_A, a, b);
+            double dyA0 = DIVDY(Ac - RAW(s_A, a, b - 1)), dyA1 = DIVDY(RAW(s_A, a, b + 1) - Ac);
+            double dxA0 = DIVDX(Ac - RAW(s_A, a - 1, b)), dxA1 = DIVDX(RAW(s_A, a + 1, b) - Ac);
+            Cc(s_Bx, a, b) = -(0.5 * (dyA0 + dyA1)) / hc;           // sw_mhd_jacobian_functions.jl:5-7
+            Cc(s_By, a, b) = (0.5 * (dxA0 + dxA1)) / hc;            // :1-3
 #else
-                Cc(s_K, a, b) = 0.25 * (fma(u0, u0, u1 * u1) + fma(v0, v0, v1 * v1));
-                double rh = frcp(hc);
-                Cc(s_Bx, a, b) = ((RAW(s_A, a, b - 1) - RAW(s_A, a, b + 1)) * (0.5 * p.rdy)) * rh;
-                Cc(s_By, a, b) = ((RAW(s_A, a + 1, b) - RAW(s_A, a - 1, b)) * (0.5 * p.rdx)) * rh;
+            Cc(s_K, a, b) = 0.25 * (fma(u0, u0, u1 * u1) + fma(v0, v0, v1 * v1));
+            double rh = frcp(hc);
+            Cc(s_Bx, a, b) = ((RAW(s_A, a, b - 1) - RAW(s_A, a, b + 1)) * (0.5 * p.rdy)) * rh;
+            Cc(s_By, a, b) = ((RAW(s_A, a + 1, b) - RAW(s_A, a - 1, b)) * (0.5 * p.rdx)) * rh;
 #endif
-            } else if constexpr (DIAG) {                            // diagnostic B^2 at faces
-                int q = t - NXF - NYF - NZ - NC;
+        };
+        // fixed passes (NZ = 481 and NC = 340 points over 256 threads): no dispatch loop, no mixed warps
+        static_assert(NZ <= 2 * NT && NC <= 2 * NT, "phase A assumes at most two passes per list");
+        task_zeta(tid);
+        task_ccc(tid);
+        if (tid + NT < NZ) task_zeta(tid + NT);
+        if (tid + NT < NC) task_ccc(tid + NT);
+        if constexpr (DIAG) {                                       // diagnostic B^2 at faces
+            for (int q = tid; q < NDG; q += NT) {
                 if (q < YP * YR) {                                  // (dyA / ℑy h)^2 at cfc, a in [3,TX+2], b in [3,TY+3]
                     int a = 3 + q % YP, b = 3 + q / YP;
                     double bx = fdiv(-DIVDY(RAW(s_A, a, b) - RAW(s_A, a, b - 1)), 0.5 * (RAW(s_h, a, b - 1) + RAW(s_h, a, b)));
@@ -456,8 +469,10 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             const double fxA = upwind_weno(&RAW(s_A, li, lj), 1, uw, eps);
             const double fyh = upwind_weno_buf(&RAW(s_h, li, lj), W, vs, eps, buf);
             const double fyA = upwind_weno_buf(&RAW(s_A, li, lj), W, vs, eps, buf);
-            FX(s_Fxh, li, lj) = p.dy * fxh; FX(s_FxA, li, lj) = p.dy * fxA;
-            FY(s_Fyh, li, lj) = p.dx * fyh; FY(s_FyA, li, lj) = p.dx * fyA;
+            // STRICT stores the fluxes Ax*u*c, Ay*v*c of the spec; FAST stores u*c, v*c and folds the
+            // metric factors (Ax/Az = 1/dx, Ay/Az = 1/dy) into the divergence.
+            FX(s_Fxh, li, lj) = FXS * fxh; FX(s_FxA, li, lj) = FXS * fxA;
+            FY(s_Fyh, li, lj) = FYS * fyh; FY(s_FyA, li, lj) = FYS * fyA;
         }
         if (tid < 32) {                                             // north row of y-faces, b = TY+3
             const int a = 3 + tid, b = TY + 3;
@@ -465,13 +480,13 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             const bool buf = ybuf(p.by, p.gj0 + j0 + TY, 3, p.NyG);
             const double fyh = upwind_weno_buf(&RAW(s_h, a, b), W, vs, eps, buf);
             const double fyA = upwind_weno_buf(&RAW(s_A, a, b), W, vs, eps, buf);
-            FY(s_Fyh, a, b) = p.dx * fyh; FY(s_FyA, a, b) = p.dx * fyA;
+            FY(s_Fyh, a, b) = FYS * fyh; FY(s_FyA, a, b) = FYS * fyA;
         } else if (tid < 32 + TY) {                                 // east column of x-faces, a = TX+3
             const int a = TX + 3, b = 3 + (tid - 32);
             const double uw = RAW(s_u, a, b);
             const double fxh = upwind_weno(&RAW(s_h, a, b), 1, uw, eps);
             const double fxA = upwind_weno(&RAW(s_A, a, b), 1, uw, eps);
-            FX(s_Fxh, a, b) = p.dy * fxh; FX(s_FxA, a, b) = p.dy * fxA;
+            FX(s_Fxh, a, b) = FXS * fxh; FX(s_FxA, a, b) = FXS * fxA;
         }
         __syncthreads();
 
@@ -526,8 +541,13 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             }
             // Gh, GA at ccc
             {
+#if SWMHD_STRICT
                 Gn2 = -(p.inv_az * ((FX(s_Fxh, li + 1, lj) - FX(s_Fxh, li, lj)) + (FY(s_Fyh, li, lj + 1) - FY(s_Fyh, li, lj))));
                 double d = p.inv_az * ((FX(s_FxA, li + 1, lj) - FX(s_FxA, li, lj)) + (FY(s_FyA, li, lj + 1) - FY(s_FyA, li, lj)));
+#else
+                Gn2 = -fma(FX(s_Fxh, li + 1, lj) - FX(s_Fxh, li, lj), p.rdx, (FY(s_Fyh, li, lj + 1) - FY(s_Fyh, li, lj)) * p.rdy);
+                double d = fma(FX(s_FxA, li + 1, lj) - FX(s_FxA, li, lj), p.rdx, (FY(s_FyA, li, lj + 1) - FY(s_FyA, li, lj)) * p.rdy);
+#endif
 #if SWMHD_STRICT
                 double dv = p.inv_az * ((p.dy * RAW(s_u, li + 1, lj) - p.dy * RAW(s_u, li, lj)) +
                                         (p.dx * RAW(s_v, li, lj + 1) - p.dx * RAW(s_v, li, lj)));
