@@ -44,7 +44,11 @@ namespace {
 #ifndef SWMHD_MINB
 #define SWMHD_MINB 3
 #endif
-constexpr int TX = 32, TY = 8, NT = 256;
+#ifndef SWMHD_TX
+#define SWMHD_TX 32
+#define SWMHD_TY 8
+#endif
+constexpr int TX = SWMHD_TX, TY = SWMHD_TY, NT = TX * TY;
 constexpr int W = TX + 6, HT = TY + 6, SZ = W * HT;        // raw tiles: [HT][W] (dense TMA box)
 constexpr int SZP = (SZ * 8 + 127) / 128 * 16;             // raw tile padded to a multiple of 128 B (TMA dst alignment)
 constexpr unsigned TILE_TX_BYTES = 4u * SZ * 8u;           // bytes one tile load brings in (4 fields)
@@ -474,14 +478,15 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             FX(s_Fxh, li, lj) = FXS * fxh; FX(s_FxA, li, lj) = FXS * fxA;
             FY(s_Fyh, li, lj) = FYS * fyh; FY(s_FyA, li, lj) = FYS * fyA;
         }
-        if (tid < 32) {                                             // north row of y-faces, b = TY+3
+        static_assert(TX <= 32 && TY <= 32, "leftover faces: north row on warp 0, east column on warp 1");
+        if (tid < TX) {                                             // north row of y-faces, b = TY+3
             const int a = 3 + tid, b = TY + 3;
             const double vs = RAW(s_v, a, b);
             const bool buf = ybuf(p.by, p.gj0 + j0 + TY, 3, p.NyG);
             const double fyh = upwind_weno_buf(&RAW(s_h, a, b), W, vs, eps, buf);
             const double fyA = upwind_weno_buf(&RAW(s_A, a, b), W, vs, eps, buf);
             FY(s_Fyh, a, b) = FYS * fyh; FY(s_FyA, a, b) = FYS * fyA;
-        } else if (tid < 32 + TY) {                                 // east column of x-faces, a = TX+3
+        } else if (tid >= 32 && tid < 32 + TY) {                    // east column of x-faces, a = TX+3
             const int a = TX + 3, b = 3 + (tid - 32);
             const double uw = RAW(s_u, a, b);
             const double fxh = upwind_weno(&RAW(s_h, a, b), 1, uw, eps);
@@ -719,9 +724,9 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
         };
         flux_uu(li - 1, lj); flux_uv(li, lj); flux_tx(li, lj);
         flux_vu(li, lj); flux_vv(li, lj - 1); flux_ty(li, lj);
-        if (tid < 32) {                                             // north row
+        if (tid < TX) {                                             // north row
             flux_vu(3 + tid, TY + 3); flux_vv(3 + tid, TY + 2); flux_ty(3 + tid, TY + 3);
-        } else if (tid < 32 + TY) {                                 // east column
+        } else if (tid >= 32 && tid < 32 + TY) {                    // east column
             const int b = 3 + (tid - 32);
             flux_uu(TX + 2, b); flux_uv(TX + 3, b); flux_tx(TX + 3, b);
         }
