@@ -147,6 +147,7 @@ def cpu_reference_rate(form, Nx, rows, steps, warmup=0):
     from swmhd_b200 import abi
     from swmhd_b200.grids import RectilinearGrid
     from oracle import pyoracle as O
+    O.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
     grid = RectilinearGrid((Nx, rows), (-5, 5), (-5 * rows / Nx, 5 * rows / Nx))
     cfg = abi.make_config(Nx, rows, Lx=grid.Lx, Ly=grid.Ly, formulation=form)
     U = initial_state(grid, form)
@@ -344,6 +345,26 @@ def run_native(args):
         achieved = ncell * BYTES_PER_CELL_UPDATE * K / (ms_total * 1e-3) / 1e9 / world
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "note": "per GPU, whole step (kernels + exchange), not a single-kernel figure"}
+        # ---- end to end at N GPUs: every rank uploads its slab from pinned host memory, halos are exchanged,
+        # one step runs and the (all-reduced) diagnostics come back to the host, per step
+        if not args.no_e2e:
+            ke = min(K, 10)
+            h2d = sum(a.nbytes for a in U0)
+            for _ in range(2):
+                sm.set_state(U0); sm.fill_halos(); sm.step_diag(dt, 1)
+            sm.synchronize(); dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(ke):
+                sm.set_state(U0)
+                sm.fill_halos()
+                d = sm.step_diag(dt, 1)
+            sm.synchronize(); dist.barrier()
+            el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+            el = float(el.item())
+            e2e = {"value": ncell * ke / el, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 9 * 8 * world,
+                   "ms_per_step": el / ke * 1e3, "steps": ke,
+                   "what": "per rank: slab upload from pinned host memory (4 haloed fields) + NCCL halo exchange + one RK3 step + diagnostics (D2H + all-reduce), per step"}
         sm.close()
 
     if rank != 0:

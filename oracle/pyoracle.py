@@ -37,6 +37,11 @@ def lib():
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """Use n OpenMP threads for the oracle (returns the number in effect)."""
+    return int(lib().swmhd_oracle_set_threads(C.c_int(int(n))))
+
+
 def _p(a):
     assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
     return a.ctypes.data_as(_dp)

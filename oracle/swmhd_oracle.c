@@ -43,6 +43,9 @@
 #include <string.h>
 #include <stdint.h>
 #include "../include/swmhd.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define H3 3
 
@@ -77,6 +80,16 @@ static void S_init(S *s, const swmhd_config *c, const double *u, const double *v
 static int rows_of(const swmhd_config *c, int field) {
     return c->Ny + 2 * H3 + ((field == SWMHD_V && c->topo_y == SWMHD_BOUNDED) ? 1 : 0);
 }
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs of bench.py ask for all cores explicitly */
+int swmhd_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n; return 1;
+#endif
+}
+
 size_t swmhd_oracle_field_len(const swmhd_config *c, int field) {
     return (size_t)(c->Nx + 2 * H3) * (size_t)rows_of(c, field);
 }
