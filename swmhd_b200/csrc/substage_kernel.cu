@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
         // smoothness; h and A at the west and the south face), so their FP64 dependency chains
         // interleave.  Warps 0/1 add the tile's north row / east column of faces.
         double adv_u, adv_v, vhat, uhat;
+        double own_u, own_v, own_fxh, own_fxA, own_fyh, own_fyA;   // carried in registers into phase C
         {
             vhat = avg4(RAW(s_v, li - 1, lj), RAW(s_v, li, lj), RAW(s_v, li - 1, lj + 1), RAW(s_v, li, lj + 1));
             uhat = avg4(RAW(s_u, li, lj - 1), RAW(s_u, li + 1, lj - 1), RAW(s_u, li, lj), RAW(s_u, li + 1, lj));
@@ -475,8 +476,10 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             const double fyA = upwind_weno_buf(&RAW(s_A, li, lj), W, vs, eps, buf);
             // STRICT stores the fluxes Ax*u*c, Ay*v*c of the spec; FAST stores u*c, v*c and folds the
             // metric factors (Ax/Az = 1/dx, Ay/Az = 1/dy) into the divergence.
-            FX(s_Fxh, li, lj) = FXS * fxh; FX(s_FxA, li, lj) = FXS * fxA;
-            FY(s_Fyh, li, lj) = FYS * fyh; FY(s_FyA, li, lj) = FYS * fyA;
+            own_u = uw; own_v = vs;
+            own_fxh = FXS * fxh; own_fxA = FXS * fxA; own_fyh = FYS * fyh; own_fyA = FYS * fyA;
+            FX(s_Fxh, li, lj) = own_fxh; FX(s_FxA, li, lj) = own_fxA;
+            FY(s_Fyh, li, lj) = own_fyh; FY(s_FyA, li, lj) = own_fyA;
         }
         static_assert(TX <= 32 && TY <= 32, "leftover faces: north row on warp 0, east column on warp 1");
         if (tid < TX) {                                             // north row of y-faces, b = TY+3
@@ -547,17 +550,17 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
             // Gh, GA at ccc
             {
 #if SWMHD_STRICT
-                Gn2 = -(p.inv_az * ((FX(s_Fxh, li + 1, lj) - FX(s_Fxh, li, lj)) + (FY(s_Fyh, li, lj + 1) - FY(s_Fyh, li, lj))));
-                double d = p.inv_az * ((FX(s_FxA, li + 1, lj) - FX(s_FxA, li, lj)) + (FY(s_FyA, li, lj + 1) - FY(s_FyA, li, lj)));
+                Gn2 = -(p.inv_az * ((FX(s_Fxh, li + 1, lj) - own_fxh) + (FY(s_Fyh, li, lj + 1) - own_fyh)));
+                double d = p.inv_az * ((FX(s_FxA, li + 1, lj) - own_fxA) + (FY(s_FyA, li, lj + 1) - own_fyA));
 #else
-                Gn2 = -fma(FX(s_Fxh, li + 1, lj) - FX(s_Fxh, li, lj), p.rdx, (FY(s_Fyh, li, lj + 1) - FY(s_Fyh, li, lj)) * p.rdy);
-                double d = fma(FX(s_FxA, li + 1, lj) - FX(s_FxA, li, lj), p.rdx, (FY(s_FyA, li, lj + 1) - FY(s_FyA, li, lj)) * p.rdy);
+                Gn2 = -fma(FX(s_Fxh, li + 1, lj) - own_fxh, p.rdx, (FY(s_Fyh, li, lj + 1) - own_fyh) * p.rdy);
+                double d = fma(FX(s_FxA, li + 1, lj) - own_fxA, p.rdx, (FY(s_FyA, li, lj + 1) - own_fyA) * p.rdy);
 #endif
 #if SWMHD_STRICT
-                double dv = p.inv_az * ((p.dy * RAW(s_u, li + 1, lj) - p.dy * RAW(s_u, li, lj)) +
-                                        (p.dx * RAW(s_v, li, lj + 1) - p.dx * RAW(s_v, li, lj)));
+                double dv = p.inv_az * ((p.dy * RAW(s_u, li + 1, lj) - p.dy * own_u) +
+                                        (p.dx * RAW(s_v, li, lj + 1) - p.dx * own_v));
 #else
-                double dv = fma(RAW(s_u, li + 1, lj) - RAW(s_u, li, lj), p.rdx, (RAW(s_v, li, lj + 1) - RAW(s_v, li, lj)) * p.rdy);
+                double dv = fma(RAW(s_u, li + 1, lj) - own_u, p.rdx, (RAW(s_v, li, lj + 1) - own_v) * p.rdy);
 #endif
                 Gn3 = -d + RAW(s_A, li, lj) * dv;
             }
