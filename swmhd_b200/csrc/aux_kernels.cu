@@ -48,8 +48,9 @@ __global__ void halo_kernel(const HaloParams p) {
     int dj = south ? 1 - kk : Ny + kk, sj = south ? kk : Ny + 1 - kk;
     double val = a[(size_t)(sj + 2) * P + si];
     if (k == 3 && p.grad) {
-        if (south) val = val - p.gs * (double)(2 * kk - 1) * p.dy;
-        else       val = val + p.gn * (double)(2 * kk - 1) * p.dy;
+        // explicit roundings (no FMA contraction): the halo must be bit-identical to the oracle's
+        if (south) val = __dsub_rn(val, __dmul_rn(__dmul_rn(p.gs, (double)(2 * kk - 1)), p.dy));
+        else       val = __dadd_rn(val, __dmul_rn(__dmul_rn(p.gn, (double)(2 * kk - 1)), p.dy));
     }
     a[(size_t)(dj + 2) * P + pi] = val;
 }

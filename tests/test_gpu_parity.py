@@ -228,3 +228,59 @@ def test_device_side_writer_outputs(kind):
     # halos of the outputs are the periodic images of their interiors (with_halos = true writers)
     assert np.array_equal(s_o[it][:, :3], s_o[3:3 + g.Ny, 3 + g.Nx:6 + g.Nx])
     assert np.array_equal(s_o[it][:3, :], s_o[3 + g.Ny:6 + g.Ny, 3:3 + g.Nx])
+
+
+@pytest.mark.parametrize("kind", ["J", "D", "BJ"])
+def test_tiny_grids_strict(kind):
+    """Smallest legal grids (a tile is larger than the whole domain; TMA boxes hang over every edge)."""
+    for (N, Ny) in [(8, 8), (16, 8), (10, 12), (34, 9)]:
+        g, cfg, U = make_case(kind, N, Ny=Ny, arith=abi.ARITH_STRICT, perturb=29)
+        Ug = run_gpu(cfg, U, 0.002, 3)
+        O.fill_halos(cfg, U)
+        O.step(cfg, U, 0.002, 3)
+        for k in range(4):
+            assert np.array_equal(Ug[k], U[k]), (N, Ny, k)
+
+
+def test_error_paths():
+    """Error behaviour of the C ABI: wrong buffer length, bad stage, bad field — no crash, an error code and a message."""
+    from swmhd_b200.context import SwmhdError
+    g, cfg, U = make_case("J", 32, Ny=16)
+    ctx = Context(cfg)
+    with pytest.raises(SwmhdError) as e:
+        ctx.set_field(abi.U, np.zeros((5, 5)))
+    assert e.value.code == abi.ERR_ARG and "length mismatch" in str(e.value)
+    with pytest.raises(SwmhdError):
+        ctx.substage(0.01, 4)
+    with pytest.raises(SwmhdError):
+        ctx.substage_interior(0.01, 1)          # edges not called first
+    with pytest.raises(SwmhdError):
+        ctx.arm_diag(5000)
+    U[abi.H][5, 5] = np.nan
+    ctx.set_state(U)
+    with pytest.raises(SwmhdError) as e:
+        ctx.diagnostics()
+    assert e.value.code == abi.ERR_NONFINITE
+    assert ctx.diagnostics(check_finite=False)["all_finite"] == 0
+    ctx.close()
+
+
+def test_fuzz_strict_bit_identity():
+    """Seeded fuzz over sizes, formulations, topologies and data: STRICT arithmetic must stay bit-identical to the
+    oracle (whole parent arrays, halos included) — catches value-dependent rounding differences."""
+    rng = np.random.default_rng(20261018)
+    for trial in range(16):
+        kind = ["J", "D", "BJ", "BD"][trial % 4]
+        N = int(rng.integers(8, 90))
+        Ny = int(rng.integers(8, 70))
+        seed = int(rng.integers(1, 10_000))
+        nst = int(rng.integers(1, 4))
+        g, cfg, U = make_case(kind, N, Ny=Ny, arith=abi.ARITH_STRICT, perturb=seed)
+        if kind.startswith("B"):
+            cfg.A_grad_south, cfg.A_grad_north = float(rng.uniform(-0.1, 0.1)), float(rng.uniform(-0.1, 0.1))
+        dt = float(rng.uniform(0.001, 0.004))
+        Ug = run_gpu(cfg, U, dt, nst)
+        O.fill_halos(cfg, U)
+        O.step(cfg, U, dt, nst)
+        for k in range(4):
+            assert np.array_equal(Ug[k], U[k]), (trial, kind, N, Ny, seed, nst, k)
