@@ -25,6 +25,7 @@ UNITS = [
     # (source, object, extra flags)
     ("substage_kernel.cu", "substage_strict.o", ["-DSWMHD_STRICT=1", "-fmad=false", "-prec-div=true", "-prec-sqrt=true"]),
     ("substage_kernel.cu", "substage_fast.o", ["-DSWMHD_STRICT=0"]),
+    ("substage_rb.cu", "substage_rb.o", []),
     ("aux_kernels.cu", "aux_kernels.o", []),
     ("swmhd_api.cu", "swmhd_api.o", []),
 ]

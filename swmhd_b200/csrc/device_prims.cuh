@@ -1,0 +1,97 @@
+// device_prims.cuh — device helpers shared by the substage kernels (sm_100a).
+//   * TMA (cp.async.bulk.tensor) + mbarrier wrappers
+//   * warp reductions
+//   * FAST-arithmetic pieces: Newton-refined reciprocal, WENO5-Z in difference form
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace swmhd {
+
+__device__ __forceinline__ double warp_sum(double x) {
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double warp_max(double x) {
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// ---- TMA + mbarrier (sm_90+/sm_100a): cp.async.bulk.tensor into shared memory ------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// L2 prefetch of a TMA box (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(tm), "r"(c0), "r"(c1) : "memory");
+}
+
+// ---- FAST arithmetic ------------------------------------------------------------------------------
+// 1/x: rcp.approx (2^-23) + two Newton steps (full double precision for normal x)
+__device__ __forceinline__ double frcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// WENO5-Z in difference form.  With the first differences d1..d4 of the five upwind
+// samples (a,b,c,d,e) the second differences and the E terms cost one operation each, and every
+// candidate is c + X_k/6 with X_0 = 4 d3 - d4, X_1 = d2 + 2 d3, X_2 = 5 d2 - 2 d1, so that
+//     sum(w_k p_k) = c + sum(alpha_k C_k X_k / 6) / sum(C_k alpha_k):   a correction to the upwind-side
+// cell value instead of a blend of O(1) numbers.
+// alpha_k = 1 + tau^2/c_k^2 (c_k = beta_k + eps) is multiplied through by prod(c_k^2): one division.
+//
+// acc_k += D_k^2 + r E_k^2 with r = (1/4)/(13/12) = 3/13: the smoothness indicators divided by 13/12.
+// The Z weights depend only on ratios tau/c_k, so a common scale of (beta_k + eps) is free: eps is scaled too.
+// The accumulators are invariant under (d1,d2,d3,d4) -> -(d1,d2,d3,d4).
+__device__ __forceinline__ void weno_beta_acc4(double d1, double d2, double d3, double d4,
+                                               double &c0, double &c1, double &c2) {
+    constexpr double r = 3.0 / 13.0;
+    const double D0 = d4 - d3, E0 = fma(-3.0, d3, d4);      // (c,d,e): c-2d+e, 3c-4d+e
+    const double D1 = d3 - d2, E1 = d2 + d3;                // (b,c,d): b-2c+d, -(b-d)
+    const double D2 = d2 - d1, E2 = fma(3.0, d2, -d1);      // (a,b,c): a-2b+c, a-4b+3c
+    c0 = fma(D0, D0, fma(r * E0, E0, c0));
+    c1 = fma(D1, D1, fma(r * E1, E1, c1));
+    c2 = fma(D2, D2, fma(r * E2, E2, c2));
+}
+// numerator and denominator of the correction: reconstruction = c + num/den (odd in d1..d4 / even)
+__device__ __forceinline__ void weno_corr4(double d1, double d2, double d3, double d4,
+                                           double c0, double c1, double c2, double &num, double &den) {
+    const double tau = c2 - c0, t2 = tau * tau;
+    const double s0 = c0 * c0, s1 = c1 * c1, s2 = c2 * c2;
+    const double q2 = s0 * s1, q0 = s1 * s2, q1 = s0 * s2, S = q2 * s2;
+    const double a0 = fma(t2, q0, S), a1 = fma(t2, q1, S), a2 = fma(t2, q2, S);
+    const double Y0 = fma(0.2, d3, -0.05 * d4);                 // 0.3/6 (4 d3 - d4)
+    const double Y1 = fma(0.2, d3, 0.1 * d2);                   // 0.6/6 (d2 + 2 d3)
+    const double Y2 = fma(1.0 / 12.0, d2, (-1.0 / 30.0) * d1);  // 0.1/6 (5 d2 - 2 d1)
+    num = fma(a0, Y0, fma(a1, Y1, a2 * Y2));
+    den = fma(0.3, a0, fma(0.6, a1, 0.1 * a2));
+}
+
+} // namespace swmhd

@@ -27,6 +27,10 @@ struct KParams {
     double *G[4];        // G^- on entry (stages 2,3), G^n on exit (stages 1,2)
     int use_tma;         // 1: tm[] are valid tensor maps of Uo[] (TMA tile loads)
     alignas(64) CUtensorMap tm[4];
+    int use_rb;          // 1: tm_rb[] are valid (row-blocked kernel, substage_rb.cu: taller TMA box)
+    int rb_ahead;        // L2 prefetch distance in tiles (CTAs in flight)
+    int row_begin, row_end;   // 0-based cell rows [row_begin, row_end) of this launch (set by the rb launcher)
+    alignas(64) CUtensorMap tm_rb[4];
     double *diag;        // per-CTA diagnostic partials [tiles][NDIAG] (stage-1 DIAG variant), or nullptr
 };
 
@@ -62,6 +66,9 @@ constexpr int NDIAG = 9; // sums: ke, me, pe, sum_h [0..3]; maxima: |u|, |A|, -h
 cudaError_t launch_substage_strict(const KParams &p, int form, int stage, cudaStream_t st);
 cudaError_t launch_substage_fast(const KParams &p, int form, int stage, cudaStream_t st);
 void substage_tile(int *tx, int *ty);
+// row-blocked variant (Jacobian form, FAST arithmetic, TMA): stages 1..3
+cudaError_t launch_substage_rb(const KParams &p, int stage, cudaStream_t st);
+void substage_rb_tile(int *tx, int *ty);
 cudaError_t launch_halo(const HaloParams &p, cudaStream_t st);
 cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st);
 cudaError_t launch_diag_final(const double *partials, int nblocks, double *stage, double *out9, cudaStream_t st);

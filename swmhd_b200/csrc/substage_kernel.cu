@@ -23,6 +23,7 @@
 //       Lorentz force, U += dt(gamma G^n + zeta G^-), store U_new and G^n.
 // HBM traffic per cell and substage: 4-8 reads + 4-8 writes of doubles (algorithmic).
 #include "kparams.h"
+#include "device_prims.cuh"
 #include <cstdlib>
 
 #ifndef SWMHD_STRICT
@@ -70,15 +71,6 @@ __device__ __forceinline__ double fdiv(double a, double b) { return a / b; }
 #define FXS p.dy
 #define FYS p.dx
 #else
-__device__ __forceinline__ double frcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
-}
 __device__ __forceinline__ double fdiv(double a, double b) { return a * frcp(b); }
 #define DIVDX(x) ((x) * p.rdx)
 #define DIVDY(x) ((x) * p.rdy)
@@ -126,37 +118,17 @@ __device__ __forceinline__ double weno5_vs(const double *qz, const double *qu, c
                       0.5 * (bu0 + bv0), 0.5 * (bu1 + bv1), 0.5 * (bu2 + bv2), eps);
 }
 #else
-// FAST WENO5-Z in difference form.  With the first differences d1..d4 of the five upwind samples
-// (a,b,c,d,e) the second differences and the E terms cost one operation each, and every candidate is
-// c + X_k/6 with X_0 = 4 d3 - d4, X_1 = d2 + 2 d3, X_2 = 5 d2 - 2 d1, so that
-//     sum(w_k p_k) = c + sum(alpha_k C_k X_k / 6) / sum(C_k alpha_k):   a correction to the upwind-side
-// cell value instead of a blend of O(1) numbers.
-// alpha_k = 1 + tau^2/c_k^2 (c_k = beta_k + eps) is multiplied through by prod(c_k^2): one division.
+// FAST WENO5-Z in difference form (device_prims.cuh).
 struct WenoDiff { double c, d1, d2, d3, d4; };
 __device__ __forceinline__ WenoDiff weno_diffs(double a, double b, double c, double d, double e) {
     WenoDiff w; w.c = c; w.d1 = b - a; w.d2 = c - b; w.d3 = d - c; w.d4 = e - d; return w;
 }
-// acc_k += D_k^2 + r E_k^2 with r = (1/4)/(13/12) = 3/13: the smoothness indicators divided by 13/12.
-// The Z weights depend only on ratios tau/c_k, so a common scale of (beta_k + eps) is free: eps is scaled too.
 __device__ __forceinline__ void weno_beta_acc(const WenoDiff &w, double &c0, double &c1, double &c2) {
-    constexpr double r = 3.0 / 13.0;
-    const double D0 = w.d4 - w.d3, E0 = fma(-3.0, w.d3, w.d4);      // (c,d,e): c-2d+e, 3c-4d+e
-    const double D1 = w.d3 - w.d2, E1 = w.d2 + w.d3;               // (b,c,d): b-2c+d, -(b-d)
-    const double D2 = w.d2 - w.d1, E2 = fma(3.0, w.d2, -w.d1);     // (a,b,c): a-2b+c, a-4b+3c
-    c0 = fma(D0, D0, fma(r * E0, E0, c0));
-    c1 = fma(D1, D1, fma(r * E1, E1, c1));
-    c2 = fma(D2, D2, fma(r * E2, E2, c2));
+    weno_beta_acc4(w.d1, w.d2, w.d3, w.d4, c0, c1, c2);
 }
 __device__ __forceinline__ double weno_blend_c(const WenoDiff &w, double c0, double c1, double c2) {
-    const double tau = c2 - c0, t2 = tau * tau;
-    const double s0 = c0 * c0, s1 = c1 * c1, s2 = c2 * c2;
-    const double q2 = s0 * s1, q0 = s1 * s2, q1 = s0 * s2, S = q2 * s2;
-    const double a0 = fma(t2, q0, S), a1 = fma(t2, q1, S), a2 = fma(t2, q2, S);
-    const double Y0 = fma(0.2, w.d3, -0.05 * w.d4);                 // 0.3/6 (4 d3 - d4)
-    const double Y1 = fma(0.2, w.d3, 0.1 * w.d2);                   // 0.6/6 (d2 + 2 d3)
-    const double Y2 = fma(1.0 / 12.0, w.d2, (-1.0 / 30.0) * w.d1);  // 0.1/6 (5 d2 - 2 d1)
-    const double num = fma(a0, Y0, fma(a1, Y1, a2 * Y2));
-    const double den = fma(0.3, a0, fma(0.6, a1, 0.1 * a2));
+    double num, den;
+    weno_corr4(w.d1, w.d2, w.d3, w.d4, c0, c1, c2, num, den);
     return fma(num, frcp(den), w.c);
 }
 __device__ __forceinline__ double weno5(double a, double b, double c, double d, double e, double eps) {
@@ -233,40 +205,6 @@ __device__ __forceinline__ double upwind_sel(double vel, double L, double R) {
 }
 
 #define RAW(arr, a, b) arr[(b) * W + (a)]
-
-__device__ __forceinline__ double warp_sum(double x) {
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    return x;
-}
-__device__ __forceinline__ double warp_max(double x) {
-    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_down_sync(0xffffffffu, x, o));
-    return x;
-}
-
-// ---- TMA + mbarrier (sm_90+/sm_100a): cp.async.bulk.tensor into shared memory ------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, uint64_t *bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
 
 // ---------------------------------------------------------------------------
 constexpr int NDG_ = YP * YR + XP * (TY + 2);   // diag scratch: sqBx (YP*YR) + sqBy (XP*(TY+2))
@@ -942,6 +880,10 @@ cudaError_t LAUNCH_NAME(const KParams &p, int form, int stage, cudaStream_t st) 
     if (p.tile_rows <= 0) return cudaSuccess;
     const bool dg = (p.diag != nullptr);
     if (dg && stage != 1) return cudaErrorInvalidValue;
+#if !SWMHD_STRICT
+    // Jacobian form with TMA: the row-blocked kernel (substage_rb.cu)
+    if (form == 0 && stage >= 1 && p.use_tma && p.use_rb) return launch_substage_rb(p, stage, st);
+#endif
     switch (form * 4 + stage) {
         case 0: return launch_one<0, 0, false>(p, st);
         case 1: return dg ? launch_one<0, 1, true>(p, st) : launch_one<0, 1, false>(p, st);

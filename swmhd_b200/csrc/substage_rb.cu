@@ -1,0 +1,582 @@
+// substage_rb.cu — row-blocked fused RK3-substage kernel (sm_100a), Jacobian formulation, FAST arithmetic.
+//
+// Same work per launch as substage_kernel.cu (calculate_tendencies! + rk3_substep! + store_tendencies!
+// for all four fields, jacobian_formulation/sw_mhd_jacobian_functions.jl:1-26 inlined; in the
+// stage-1 DIAG variant also the diagnostics of SWMHD_example.jl:47-77), different thread mapping:
+//
+//   * a CTA owns a 32 x RB_TY tile, a WARP owns RB_R consecutive rows of it, a THREAD one column of
+//     those rows (RB_R cells).  Everything differenced or reconstructed along y (the vorticity
+//     reconstruction with its two velocity-stencil smoothness fields, the h and A fluxes through the
+//     y faces) is fed from a register window of the thread's column: (R+5)/R shared-memory loads per
+//     cell and stencil instead of 5, first differences shared between neighbouring faces.
+//   * the upwind side of a register window is chosen by SELECTING mirrored first differences
+//     (the smoothness indicators are even, the correction is odd in them), bit-identical to
+//     reconstructing the mirrored samples.
+//   * after the derived staggered fields (phase A, CTA-wide) warps never meet again: the east-face
+//     fluxes travel by warp shuffle, the tile's east column of faces is a per-warp pre-pass, every
+//     warp evaluates its own north face.  One __syncthreads per tile (three more in the DIAG variant).
+//
+// The shared-memory operand traffic drops from ~138 to ~85 accesses per cell-substage, which is what
+// bound the one-thread-per-cell kernel together with the FP64 pipe (profiles/README.md).
+// Arithmetic per value is the FAST arithmetic of substage_kernel.cu (same operation order).
+#include "kparams.h"
+#include "device_prims.cuh"
+#include <cstdlib>
+#include <cmath>
+
+namespace swmhd {
+namespace {
+
+#ifndef RB_TY
+#define RB_TY 16
+#endif
+#ifndef RB_R
+#define RB_R 4
+#endif
+#ifndef RB_MINB
+#define RB_MINB 3
+#endif
+#ifndef RB_L2_PREFETCH
+#define RB_L2_PREFETCH 1
+#endif
+constexpr int TX = 32, TYB = RB_TY, R = RB_R, NW = TYB / R, NT = 32 * NW;
+static_assert(TYB % R == 0 && TYB % 8 == 0, "tile rows: multiple of the rows per warp and of the 8-row launch granularity");
+static_assert((R & (R - 1)) == 0 && 2 * R <= 32, "rows per warp: power of two");
+constexpr int W = TX + 6, HT = TYB + 6, SZ = W * HT;       // raw tiles: [HT][W] (dense TMA box)
+constexpr int SZP = (SZ * 8 + 127) / 128 * 16;             // padded to a multiple of 128 B (TMA dst alignment)
+constexpr unsigned TILE_TX_BYTES = 4u * SZ * 8u;
+constexpr int ZP = TX + 5, ZR = TYB + 5;                   // ffc points a in [1,TX+5], b in [1,TYB+5]
+constexpr int CP = TX + 2, CR = TYB + 2;                   // ccc points a in [2,TX+3], b in [2,TYB+3]
+constexpr int NZ = ZP * ZR, NC = CP * CR;
+constexpr int o_z = 0, o_ut = NZ, o_vt = 2 * NZ, o_K = 3 * NZ, o_Bx = o_K + NC, o_By = o_Bx + NC;
+constexpr int DERIVED = o_By + NC;
+// DIAG: squared face B fields, aliased onto the (dead) zeta arrays
+constexpr int QXP = TX, QXR = TYB + 1;                     // (dyA/ℑy h)^2 at cfc: a in [3,TX+2], b in [3,TYB+3]
+constexpr int QYP = TX + 1, QYR = TYB + 2;                 // (dxA/ℑx h)^2 at fcc: a in [3,TX+3], b in [2,TYB+3]
+static_assert(QXP * QXR + QYP * QYR + NW * NDIAG <= 3 * NZ, "diag scratch must fit in the zeta arrays");
+constexpr size_t SMEM_BYTES = ((size_t)4 * SZP + DERIVED) * sizeof(double) + 16;
+
+#define RAW(arr, a, b) arr[(b) * W + (a)]
+#define Zf(arr, a, b) arr[((b) - 1) * ZP + (a) - 1]
+#define Cc(arr, a, b) arr[((b) - 2) * CP + (a) - 2]
+
+__device__ __forceinline__ double avg4(double a, double b, double c, double d) { return 0.25 * ((a + b) + (c + d)); }
+__device__ __forceinline__ double sym2(double b, double c) { return 0.5 * (b + c); }
+// Bounded-y wall buffer (oracle ybuf): footprint f-n..f+n-1 must stay in [1,hi]
+__device__ __forceinline__ bool ybuf(int by, int f, int n, int hi) { return by && (f - n < 1 || f + n - 1 > hi); }
+
+// ---- WENO5-Z from shared memory (x direction): pointer-selected upwind stencil --------------------
+__device__ __forceinline__ double weno5_mem(const double *q, int s, double es) {
+    const double a = q[0], b = q[s], c = q[2 * s], d = q[3 * s], e = q[4 * s];
+    const double d1 = b - a, d2 = c - b, d3 = d - c, d4 = e - d;
+    double c0 = es, c1 = es, c2 = es, num, den;
+    weno_beta_acc4(d1, d2, d3, d4, c0, c1, c2);
+    weno_corr4(d1, d2, d3, d4, c0, c1, c2, num, den);
+    return fma(num, frcp(den), c);
+}
+// vel * psi_upwind at face f (ctr = &psi[f]): left-biased psi[f-3..f+1] for vel > 0, else the mirror
+__device__ __forceinline__ double upwind_weno_mem(const double *ctr, double vel, double eps) {
+    const bool pos = vel > 0.0;
+    return vel * weno5_mem(pos ? ctr - 3 : ctr + 2, pos ? 1 : -1, eps * (12.0 / 13.0));
+}
+// zeta with VelocityStencil smoothness (beta = (beta[ℑy u] + beta[ℑx v]) / 2, common scale 13/24)
+__device__ __forceinline__ double weno5_vs_mem(const double *qz, const double *qu, const double *qv, int s, double eps) {
+    const double es = eps * (24.0 / 13.0);
+    double c0 = es, c1 = es, c2 = es, num, den;
+    {
+        const double a = qu[0], b = qu[s], c = qu[2 * s], d = qu[3 * s], e = qu[4 * s];
+        weno_beta_acc4(b - a, c - b, d - c, e - d, c0, c1, c2);
+    }
+    {
+        const double a = qv[0], b = qv[s], c = qv[2 * s], d = qv[3 * s], e = qv[4 * s];
+        weno_beta_acc4(b - a, c - b, d - c, e - d, c0, c1, c2);
+    }
+    const double a = qz[0], b = qz[s], c = qz[2 * s], d = qz[3 * s], e = qz[4 * s];
+    weno_corr4(b - a, c - b, d - c, e - d, c0, c1, c2, num, den);
+    return fma(num, frcp(den), c);
+}
+
+// ---- WENO5-Z from a sliding register window (y direction) -------------------------------------------
+// The window holds psi[f-3..f+2] = q0..q5 along the thread's column as first differences
+// D[k] = q[k+1]-q[k] plus the samples q2..q5.  Left-biased (pos): samples q0..q4, differences
+// (D0,D1,D2,D3), centre q2.  Right-biased: samples q5..q1, whose differences are -(D4,D3,D2,D1),
+// centre q3: the indicators are even in the differences, the correction is odd — selecting the
+// differences is bit-identical to reconstructing the mirrored samples.
+struct Win { double q2, q3, q4, q5, D0, D1, D2, D3, D4; };
+struct WinD { double last, D0, D1, D2, D3, D4; };           // smoothness-only field: differences + newest sample
+__device__ __forceinline__ void win_load(Win &w, const double *p0, int st) {   // p0 = &psi[f-3]
+    const double q0 = p0[0], q1 = p0[st];
+    w.q2 = p0[2 * st]; w.q3 = p0[3 * st]; w.q4 = p0[4 * st]; w.q5 = p0[5 * st];
+    w.D0 = q1 - q0; w.D1 = w.q2 - q1; w.D2 = w.q3 - w.q2; w.D3 = w.q4 - w.q3; w.D4 = w.q5 - w.q4;
+}
+__device__ __forceinline__ void win_load(WinD &w, const double *p0, int st) {
+    const double q0 = p0[0], q1 = p0[st], q2 = p0[2 * st], q3 = p0[3 * st], q4 = p0[4 * st];
+    w.last = p0[5 * st];
+    w.D0 = q1 - q0; w.D1 = q2 - q1; w.D2 = q3 - q2; w.D3 = q4 - q3; w.D4 = w.last - q4;
+}
+__device__ __forceinline__ void win_push(Win &w, double n) {                   // f -> f+1
+    w.D0 = w.D1; w.D1 = w.D2; w.D2 = w.D3; w.D3 = w.D4; w.D4 = n - w.q5;
+    w.q2 = w.q3; w.q3 = w.q4; w.q4 = w.q5; w.q5 = n;
+}
+__device__ __forceinline__ void win_push(WinD &w, double n) {
+    w.D0 = w.D1; w.D1 = w.D2; w.D2 = w.D3; w.D3 = w.D4; w.D4 = n - w.last; w.last = n;
+}
+#define SEL4(pos, w) (pos) ? (w).D0 : (w).D4, (pos) ? (w).D1 : (w).D3, (w).D2, (pos) ? (w).D3 : (w).D1
+__device__ __forceinline__ double weno5_win(bool pos, const Win &w, double es) {
+    double c0 = es, c1 = es, c2 = es, num, den;
+    weno_beta_acc4(SEL4(pos, w), c0, c1, c2);
+    weno_corr4(SEL4(pos, w), c0, c1, c2, num, den);
+    return fma(pos ? num : -num, frcp(den), pos ? w.q2 : w.q3);
+}
+__device__ __forceinline__ double weno5_vs_win(bool pos, const Win &z, const WinD &u, const WinD &v, double eps) {
+    const double es = eps * (24.0 / 13.0);
+    double c0 = es, c1 = es, c2 = es, num, den;
+    weno_beta_acc4(SEL4(pos, u), c0, c1, c2);
+    weno_beta_acc4(SEL4(pos, v), c0, c1, c2);
+    weno_corr4(SEL4(pos, z), c0, c1, c2, num, den);
+    return fma(pos ? num : -num, frcp(den), pos ? z.q2 : z.q3);
+}
+
+// ---- batched forms: N independent reconstructions advanced in lock-step ---------------------------
+// The FP64 pipe of an SM sustains its peak only when a warp offers >= 4 independent instructions in a
+// row (tools/micro/fp64_pipe.cu: 2.17 cycles per warp instruction at ILP 4, 3.0 at ILP 1 with any
+// number of warps; dependent-issue latency 8 cycles).  ptxas keeps the source order of independent
+// chains, so the chains are interleaved here, statement by statement.  Arithmetic per chain is that of
+// weno_beta_acc4 / weno_corr4 / frcp.
+#define FORN _Pragma("unroll") for (int n = 0; n < N; n++)
+template <int N>
+__device__ __forceinline__ void beta_acc_n(const double (&d1)[N], const double (&d2)[N], const double (&d3)[N], const double (&d4)[N],
+                                           double (&c0)[N], double (&c1)[N], double (&c2)[N]) {
+    constexpr double r = 3.0 / 13.0;
+    double D0[N], E0[N], D1[N], E1[N], D2[N], E2[N];
+    FORN D0[n] = d4[n] - d3[n];
+    FORN E0[n] = fma(-3.0, d3[n], d4[n]);
+    FORN D1[n] = d3[n] - d2[n];
+    FORN E1[n] = d2[n] + d3[n];
+    FORN D2[n] = d2[n] - d1[n];
+    FORN E2[n] = fma(3.0, d2[n], -d1[n]);
+    double t0[N], t1[N], t2[N];
+    FORN t0[n] = r * E0[n];
+    FORN t1[n] = r * E1[n];
+    FORN t2[n] = r * E2[n];
+    FORN t0[n] = fma(t0[n], E0[n], c0[n]);
+    FORN t1[n] = fma(t1[n], E1[n], c1[n]);
+    FORN t2[n] = fma(t2[n], E2[n], c2[n]);
+    FORN c0[n] = fma(D0[n], D0[n], t0[n]);
+    FORN c1[n] = fma(D1[n], D1[n], t1[n]);
+    FORN c2[n] = fma(D2[n], D2[n], t2[n]);
+}
+template <int N>
+__device__ __forceinline__ void corr_n(const double (&d1)[N], const double (&d2)[N], const double (&d3)[N], const double (&d4)[N],
+                                       const double (&c0)[N], const double (&c1)[N], const double (&c2)[N],
+                                       double (&num)[N], double (&den)[N]) {
+    double tau[N], s0[N], s1[N], s2[N], q0[N], q1[N], q2[N], S[N], Y0[N], Y1[N], Y2[N];
+    FORN tau[n] = c2[n] - c0[n];
+    FORN s0[n] = c0[n] * c0[n];
+    FORN s1[n] = c1[n] * c1[n];
+    FORN s2[n] = c2[n] * c2[n];
+    FORN Y0[n] = -0.05 * d4[n];
+    FORN Y1[n] = 0.1 * d2[n];
+    FORN Y2[n] = (-1.0 / 30.0) * d1[n];
+    FORN tau[n] = tau[n] * tau[n];
+    FORN q2[n] = s0[n] * s1[n];
+    FORN q0[n] = s1[n] * s2[n];
+    FORN q1[n] = s0[n] * s2[n];
+    FORN Y0[n] = fma(0.2, d3[n], Y0[n]);                         // 0.3/6 (4 d3 - d4)
+    FORN Y1[n] = fma(0.2, d3[n], Y1[n]);                         // 0.6/6 (d2 + 2 d3)
+    FORN Y2[n] = fma(1.0 / 12.0, d2[n], Y2[n]);                  // 0.1/6 (5 d2 - 2 d1)
+    FORN S[n] = q2[n] * s2[n];
+    FORN q0[n] = fma(tau[n], q0[n], S[n]);                       // a0
+    FORN q1[n] = fma(tau[n], q1[n], S[n]);                       // a1
+    FORN q2[n] = fma(tau[n], q2[n], S[n]);                       // a2
+    FORN num[n] = q2[n] * Y2[n];
+    FORN den[n] = 0.1 * q2[n];
+    FORN num[n] = fma(q1[n], Y1[n], num[n]);
+    FORN den[n] = fma(0.6, q1[n], den[n]);
+    FORN num[n] = fma(q0[n], Y0[n], num[n]);
+    FORN den[n] = fma(0.3, q0[n], den[n]);
+}
+template <int N>
+__device__ __forceinline__ void rcp_n(const double (&x)[N], double (&r)[N]) {
+    double e[N];
+    FORN asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[n]) : "d"(x[n]));
+    FORN e[n] = fma(-x[n], r[n], 1.0);
+    FORN r[n] = fma(r[n], e[n], r[n]);
+    FORN e[n] = fma(-x[n], r[n], 1.0);
+    FORN r[n] = fma(r[n], e[n], r[n]);
+}
+// first differences of the five upwind samples of a shared-memory line (pointer-selected side)
+__device__ __forceinline__ void diffs_mem(const double *q, int s, double &d1, double &d2, double &d3, double &d4, double &c) {
+    const double a = q[0], b = q[s], e = q[4 * s], d = q[3 * s];
+    c = q[2 * s];
+    d1 = b - a; d2 = c - b; d3 = d - c; d4 = e - d;
+}
+__device__ __forceinline__ void diffs_mem(const double *q, int s, double &d1, double &d2, double &d3, double &d4) {
+    double c; diffs_mem(q, s, d1, d2, d3, d4, c);
+}
+#define SELW(pos, w, n) d1[n] = (pos) ? (w).D0 : (w).D4; d2[n] = (pos) ? (w).D1 : (w).D3; d3[n] = (w).D2; d4[n] = (pos) ? (w).D3 : (w).D1
+
+// STAGE 1,2,3.  DIAG only with STAGE 1.
+template <int STAGE, bool DIAG>
+__global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_constant__ KParams p) {
+    // 128-byte aligned for the TMA destination; used directly so that the compiler keeps the shared
+    // address space (LDS/STS instead of generic LD/ST).
+    extern __shared__ __align__(128) unsigned char smem_bytes[];
+    double *const s_u = reinterpret_cast<double *>(smem_bytes);
+    double *const s_v = s_u + SZP, *const s_h = s_u + 2 * SZP, *const s_A = s_u + 3 * SZP;
+    double *const smem = s_u + 4 * SZP;
+    double *const s_z = smem + o_z, *const s_ut = smem + o_ut, *const s_vt = smem + o_vt;
+    double *const s_K = smem + o_K, *const s_Bx = smem + o_Bx, *const s_By = smem + o_By;
+    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + DERIVED);
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int Nx = p.Nx, P = p.P;
+    const double eps = p.eps;
+    const int tiles_x = (Nx + TX - 1) / TX;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int row0 = p.row_begin + tile_y * TYB;            // 0-based first cell row = parent row of b = 0
+
+    // ---- P0: stage u,v,h,A with a 3-cell halo: four TMA boxes of (TX+6) x (TYB+6) doubles ----------
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(mbar, TILE_TX_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; k++) tma_load_2d(s_u + k * SZP, &p.tm_rb[k], tile_x * TX, row0, mbar);
+#if RB_L2_PREFETCH
+        // pull the tile that the CTA taking over this slot will load into L2 now (CTAs are dispatched in
+        // blockIdx order): its TMA wait then costs an L2 hit instead of an HBM round trip
+        const int nxt = blockIdx.x + p.rb_ahead;
+        if (nxt < gridDim.x) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) tma_prefetch_2d(&p.tm_rb[k], (nxt % tiles_x) * TX, p.row_begin + (nxt / tiles_x) * TYB);
+        }
+#endif
+    }
+    const int li = lane + 3, lj0 = 3 + wp * R;              // tile-local column / first row of this thread
+    const int i = tile_x * TX + 1 + lane;                   // logical (1-based) column
+    const int jc0 = row0 + 1 + wp * R;                      // logical (1-based, slab-local) first row
+    const int gj0 = p.gj0 + jc0;                            // global row of the first cell (wall logic)
+    double Gq0 = 0.0, Gq1 = 0.0, Gq2 = 0.0, Gq3 = 0.0;      // G^- of the row in flight (software-pipelined global loads)
+    if constexpr (STAGE >= 2) {
+        if ((i <= Nx) && (jc0 <= p.row_end)) {               // first row: in flight during the tile wait and phase A
+            const size_t g0 = (size_t)(i + 2) + (size_t)P * (size_t)(jc0 + 2);
+            Gq0 = p.G[0][g0]; Gq1 = p.G[1][g0]; Gq2 = p.G[2][g0]; Gq3 = p.G[3][g0];
+        }
+    }
+    __syncthreads();                                        // barrier initialised before anybody polls it
+    mbar_wait(mbar, 0);
+
+    // ---- A: derived staggered fields, each point once per tile --------------------------------------
+#pragma unroll 4
+    for (int q = tid; q < NZ; q += NT) {                    // zeta, ℑy u, ℑx v at ffc
+        const int a = 1 + q % ZP, b = 1 + q / ZP;
+        const double vc = RAW(s_v, a, b), vw = RAW(s_v, a - 1, b), uc = RAW(s_u, a, b), us = RAW(s_u, a, b - 1);
+        s_z[q] = fma(vc - vw, p.rdx, (us - uc) * p.rdy);
+        s_ut[q] = 0.5 * (us + uc);
+        s_vt[q] = 0.5 * (vw + vc);
+    }
+#pragma unroll 3
+    for (int q = tid; q < NC; q += NT) {                    // K, Bx, By at ccc (sw_mhd_jacobian_functions.jl:1-7)
+        const int a = 2 + q % CP, b = 2 + q / CP;
+        const double u0 = RAW(s_u, a, b), u1 = RAW(s_u, a + 1, b), v0 = RAW(s_v, a, b), v1 = RAW(s_v, a, b + 1);
+        s_K[q] = 0.25 * (fma(u0, u0, u1 * u1) + fma(v0, v0, v1 * v1));
+        const double rh = frcp(RAW(s_h, a, b));
+        s_Bx[q] = ((RAW(s_A, a, b - 1) - RAW(s_A, a, b + 1)) * (0.5 * p.rdy)) * rh;
+        s_By[q] = ((RAW(s_A, a + 1, b) - RAW(s_A, a - 1, b)) * (0.5 * p.rdx)) * rh;
+    }
+    __syncthreads();
+
+    // ---- B/C: warp-private from here on --------------------------------------------------------------
+
+    // B0: the tile's east column of x faces for this warp's rows: lanes 0..R-1 take h, lanes R..2R-1 take A
+    double eastF = 0.0;
+    if (lane < 2 * R) {
+        const int b = lj0 + (lane & (R - 1));
+        const double *arr = (lane < R) ? s_h : s_A;
+        eastF = upwind_weno_mem(&RAW(arr, TX + 3, b), RAW(s_u, TX + 3, b), eps);
+    }
+
+    // Sliding windows along the own column: rows lj-2 .. lj+3 around the current row lj.  They feed the
+    // vorticity reconstruction to the centre of row lj (faces lj-2..lj+3) and the h, A fluxes through
+    // the NORTH face lj+1 of that row (samples lj-2..lj+3).  Iteration it = -1 only produces the south
+    // face of the warp's first row.
+    Win wz, wh, wA;
+    WinD wu, wv;
+    win_load(wz, &Zf(s_z, li, lj0 - 3), ZP);     // (row lj0-3 of warp 0 lies outside the zeta arrays: it is read from
+    win_load(wu, &Zf(s_ut, li, lj0 - 3), ZP);    //  valid shared memory and shifted out before the window is used)
+    win_load(wv, &Zf(s_vt, li, lj0 - 3), ZP);
+    win_load(wh, &RAW(s_h, li, lj0 - 3), W);
+    win_load(wA, &RAW(s_A, li, lj0 - 3), W);
+    double vC = RAW(s_v, li, lj0 - 1), vW = RAW(s_v, li - 1, lj0 - 1);
+    double fyh_s = 0.0, fyA_s = 0.0;
+    double dg[NDIAG];
+    if constexpr (DIAG) {
+#pragma unroll
+        for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
+        dg[6] = -INFINITY;
+    }
+    (void)dg;
+
+#pragma unroll 1
+    for (int it = -1; it < R; ++it) {
+        const int lj = lj0 + it;
+        const int j = jc0 + it, gj = gj0 + it;
+        const bool active = (i <= Nx) && (j <= p.row_end);
+        const size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(j + 2);
+        // G^- of this row was requested one iteration ago (row 0: before the tile wait); request the next row
+        const double Gm0 = Gq0, Gm1 = Gq1, Gm2 = Gq2, Gm3 = Gq3;
+        if constexpr (STAGE >= 2) {
+            if (it >= 0 && it + 1 < R && (i <= Nx) && (j + 1 <= p.row_end)) {
+                const size_t gn = gcell + (size_t)P;
+                Gq0 = p.G[0][gn]; Gq1 = p.G[1][gn]; Gq2 = p.G[2][gn]; Gq3 = p.G[3][gn];
+            }
+        }
+        const double vN = RAW(s_v, li, lj + 1), vWn = RAW(s_v, li - 1, lj + 1);
+        const bool posN = vN > 0.0, bufN = ybuf(p.by, gj + 1, 3, p.NyG);
+        const double es1 = eps * (12.0 / 13.0), es2 = eps * (24.0 / 13.0);
+        double fyh_n, fyA_n;
+        if (it < 0) {
+            // south face of the warp's first row: h and A fluxes from the windows
+            double d1[2], d2[2], d3[2], d4[2], c0[2] = {es1, es1}, c1[2] = {es1, es1}, c2[2] = {es1, es1}, num[2], den[2], rc[2];
+            SELW(posN, wh, 0); SELW(posN, wA, 1);
+            beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
+            corr_n<2>(d1, d2, d3, d4, c0, c1, c2, num, den);
+            rcp_n<2>(den, rc);
+            const double wh_ = vN * fma(posN ? num[0] : -num[0], rc[0], posN ? wh.q2 : wh.q3);
+            const double wA_ = vN * fma(posN ? num[1] : -num[1], rc[1], posN ? wA.q2 : wA.q3);
+            fyh_n = bufN ? vN * sym2(wh.q2, wh.q3) : wh_;
+            fyA_n = bufN ? vN * sym2(wA.q2, wA.q3) : wA_;
+        } else {
+            const double vhat = avg4(vW, vC, vWn, vN);
+            const double uw = RAW(s_u, li, lj), ue = RAW(s_u, li + 1, lj);
+            const double uhat = avg4(RAW(s_u, li, lj - 1), RAW(s_u, li + 1, lj - 1), uw, ue);
+            const bool posv = vhat > 0.0, posu = uhat > 0.0, posx = uw > 0.0;
+            const int offx = (lj - 1) * ZP + (posu ? li - 2 : li + 3) - 1;   // zeta to the centre i along x
+            const int sx = posu ? 1 : -1;
+            const double *qh = posx ? &RAW(s_h, li - 3, lj) : &RAW(s_h, li + 2, lj);
+            const double *qA = posx ? &RAW(s_A, li - 3, lj) : &RAW(s_A, li + 2, lj);
+            const int sp = posx ? 1 : -1;
+            double rc[8], num2[2], num4[4], cz1, ch2, cA3;
+            {   // vorticity pair: [0] to the centre of row lj along y (windows), [1] to the centre i along x (memory);
+                // VelocityStencil smoothness: beta accumulated over ℑy u and ℑx v
+                double d1[2], d2[2], d3[2], d4[2], c0[2] = {es2, es2}, c1[2] = {es2, es2}, c2[2] = {es2, es2}, den[2];
+                SELW(posv, wu, 0); diffs_mem(s_ut + offx, sx, d1[1], d2[1], d3[1], d4[1]);
+                beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
+                SELW(posv, wv, 0); diffs_mem(s_vt + offx, sx, d1[1], d2[1], d3[1], d4[1]);
+                beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
+                SELW(posv, wz, 0); diffs_mem(s_z + offx, sx, d1[1], d2[1], d3[1], d4[1], cz1);
+                corr_n<2>(d1, d2, d3, d4, c0, c1, c2, num2, den);
+                rc[0] = den[0]; rc[1] = den[1];
+            }
+            {   // flux quartet: h, A through the north face (windows), h, A through the west face (memory)
+                double d1[4], d2[4], d3[4], d4[4], c0[4] = {es1, es1, es1, es1}, c1[4] = {es1, es1, es1, es1}, c2[4] = {es1, es1, es1, es1}, den[4];
+                SELW(posN, wh, 0); SELW(posN, wA, 1);
+                diffs_mem(qh, sp, d1[2], d2[2], d3[2], d4[2], ch2);
+                diffs_mem(qA, sp, d1[3], d2[3], d3[3], d4[3], cA3);
+                beta_acc_n<4>(d1, d2, d3, d4, c0, c1, c2);
+                corr_n<4>(d1, d2, d3, d4, c0, c1, c2, num4, den);
+                rc[2] = den[0]; rc[3] = den[1]; rc[4] = den[2]; rc[5] = den[3];
+            }
+            const double hc = wh.q2, hw_ = RAW(s_h, li - 1, lj), hs = RAW(s_h, li, lj - 1);
+            rc[6] = 0.5 * (hw_ + hc);                                   // ℑx h
+            rc[7] = 0.5 * (hs + hc);                                    // ℑy h
+            {
+                double x[8];
+#pragma unroll
+                for (int n = 0; n < 8; n++) x[n] = rc[n];
+                rcp_n<8>(x, rc);
+            }
+            const double zy = fma(posv ? num2[0] : -num2[0], rc[0], posv ? wz.q2 : wz.q3);
+            const double zx = fma(num2[1], rc[1], cz1);
+            const double wh_ = vN * fma(posN ? num4[0] : -num4[0], rc[2], posN ? wh.q2 : wh.q3);
+            const double wA_ = vN * fma(posN ? num4[1] : -num4[1], rc[3], posN ? wA.q2 : wA.q3);
+            const double fxh = uw * fma(num4[2], rc[4], ch2);
+            const double fxA = uw * fma(num4[3], rc[5], cA3);
+            fyh_n = bufN ? vN * sym2(wh.q2, wh.q3) : wh_;
+            fyA_n = bufN ? vN * sym2(wA.q2, wA.q3) : wA_;
+            const double adv_u = vhat * (ybuf(p.by, gj + 1, 3, p.NyG + 1) ? sym2(wz.q2, wz.q3) : zy);
+            const double adv_v = uhat * zx;
+            // east faces: the neighbour lane's west face; lane 31 takes the pre-pass value
+            double fxh_e = __shfl_down_sync(0xffffffffu, fxh, 1), fxA_e = __shfl_down_sync(0xffffffffu, fxA, 1);
+            const double eh = __shfl_sync(0xffffffffu, eastF, it), eA = __shfl_sync(0xffffffffu, eastF, R + it);
+            if (lane == 31) { fxh_e = eh; fxA_e = eA; }
+
+            double Gn0, Gn1, Gn2, Gn3;
+            const double Ac = wA.q2, An = wA.q3, As = RAW(s_A, li, lj - 1);
+            const double Aw = RAW(s_A, li - 1, lj), Awn = RAW(s_A, li - 1, lj + 1), Aws = RAW(s_A, li - 1, lj - 1);
+            {   // Gu at fcc — lorentz_force_func_x, sw_mhd_jacobian_functions.jl:10-13,20-22 — and
+                // Gv at cfc — lorentz_force_func_y, :15-18,24-26 — advanced together
+                const double Kc = Cc(s_K, li, lj);
+                const double dKx = (Kc - Cc(s_K, li - 1, lj)) * p.rdx;
+                const double dKy = (Kc - Cc(s_K, li, lj - 1)) * p.rdy;
+                const double pgx = p.g * ((hc - hw_) * p.rdx);
+                const double pgy = p.g * ((hc - hs) * p.rdy);
+                const double dxA = (Ac - Aw) * p.rdx;
+                const double dyA = (Ac - As) * p.rdy;
+                // ℑxy(∂y F) telescopes to (F(i-1,j+1) + F(i,j+1) - F(i-1,j-1) - F(i,j-1)) / (4 dy)
+                const double m1x = ((Cc(s_Bx, li - 1, lj + 1) + Cc(s_Bx, li, lj + 1)) - (Cc(s_Bx, li - 1, lj - 1) + Cc(s_Bx, li, lj - 1))) * (0.25 * p.rdy);
+                const double m1y = ((RAW(s_A, li + 1, lj - 1) + RAW(s_A, li + 1, lj)) - (Aws + Aw)) * (0.25 * p.rdx);
+                const double m2x = ((Awn + An) - (Aws + As)) * (0.25 * p.rdy);
+                const double m2y = ((Cc(s_By, li + 1, lj - 1) + Cc(s_By, li + 1, lj)) - (Cc(s_By, li - 1, lj - 1) + Cc(s_By, li - 1, lj))) * (0.25 * p.rdx);
+                const double jacx = fma(dxA, m1x, -(m2x * ((Cc(s_Bx, li, lj) - Cc(s_Bx, li - 1, lj)) * p.rdx)));
+                const double jacy = fma(m1y, (Cc(s_By, li, lj) - Cc(s_By, li, lj - 1)) * p.rdy, -(dyA * m2y));
+                Gn0 = fma(jacx, rc[6], fma(p.f, vhat, (adv_u - dKx) - pgx));
+                Gn1 = fma(jacy, rc[7], fma(-p.f, uhat, (-adv_v - dKy) - pgy));
+                if (p.by && gj < 2) Gn1 = 0.0;                          // wall rows of a Bounded-y grid keep v = 0
+            }
+            {   // Gh, GA at ccc: flux divergences (metric factors folded in: Ax/Az = 1/dx, Ay/Az = 1/dy)
+                Gn2 = -fma(fxh_e - fxh, p.rdx, (fyh_n - fyh_s) * p.rdy);
+                const double d = fma(fxA_e - fxA, p.rdx, (fyA_n - fyA_s) * p.rdy);
+                const double dv = fma(ue - uw, p.rdx, (vN - vC) * p.rdy);
+                Gn3 = -d + Ac * dv;
+            }
+            // ---- RK3 substep + stores --------------------------------------------------------------
+            if (active) {
+                const double Gn[4] = {Gn0, Gn1, Gn2, Gn3};
+                const double Gm[4] = {Gm0, Gm1, Gm2, Gm3};
+                const double Uc[4] = {uw, vC, hc, Ac};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if constexpr (STAGE == 1) {
+                        p.Un[k][gcell] = Uc[k] + p.dtgam * Gn[k];
+                        p.G[k][gcell] = Gn[k];
+                    } else {
+                        p.Un[k][gcell] = Uc[k] + p.dt * (p.gam * Gn[k] + p.zet * Gm[k]);
+                        if constexpr (STAGE == 2) p.G[k][gcell] = Gn[k];
+                    }
+                }
+            }
+        }
+        // slide to the next row
+        fyh_s = fyh_n; fyA_s = fyA_n; vC = vN; vW = vWn;
+        if (it + 1 < R) {
+            const int bn = lj + 4;
+            win_push(wz, Zf(s_z, li, bn)); win_push(wu, Zf(s_ut, li, bn)); win_push(wv, Zf(s_vt, li, bn));
+            win_push(wh, RAW(s_h, li, bn)); win_push(wA, RAW(s_A, li, bn));
+        }
+    }
+
+    // ---- fused diagnostics of the state at the start of the step --------------------------
+    if constexpr (DIAG) {
+        double *const s_sqBx = smem, *const s_sqBy = smem + QXP * QXR, *const s_red = s_sqBy + QYP * QYR;
+        __syncthreads();                                    // every warp is done with the zeta arrays
+        for (int q = tid; q < QXP * QXR; q += NT) {          // (dyA / ℑy h)^2 at cfc
+            const int a = 3 + q % QXP, b = 3 + q / QXP;
+            const double bx = -((RAW(s_A, a, b) - RAW(s_A, a, b - 1)) * p.rdy) * frcp(0.5 * (RAW(s_h, a, b - 1) + RAW(s_h, a, b)));
+            s_sqBx[q] = bx * bx;
+        }
+        for (int q = tid; q < QYP * QYR; q += NT) {          // (dxA / ℑx h)^2 at fcc
+            const int a = 3 + q % QYP, b = 2 + q / QYP;
+            const double by_ = ((RAW(s_A, a, b) - RAW(s_A, a - 1, b)) * p.rdx) * frcp(0.5 * (RAW(s_h, a - 1, b) + RAW(s_h, a, b)));
+            s_sqBy[q] = by_ * by_;
+        }
+        __syncthreads();
+        auto sq = [](double x) { return x * x; };
+        auto SQBX = [&](int a, int b) { return s_sqBx[(b - 3) * QXP + a - 3]; };
+        auto SQBY = [&](int a, int b) { return s_sqBy[(b - 2) * QYP + a - 3]; };
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int lj = lj0 + r, j = jc0 + r;
+            if ((i <= Nx) && (j <= p.row_end)) {
+                const double hh = RAW(s_h, li, lj), aa = RAW(s_A, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj);
+                // KE bracket u^2 + ℑxyᶠᶜᵃ(v^2) at fcc(i) and fcc(i+1), averaged to the centre
+                auto keb = [&](int a) {
+                    return sq(RAW(s_u, a, lj)) + avg4(sq(RAW(s_v, a - 1, lj)), sq(RAW(s_v, a, lj)), sq(RAW(s_v, a - 1, lj + 1)), sq(RAW(s_v, a, lj + 1)));
+                };
+                dg[0] += (0.5 * hh) * (0.5 * (keb(li) + keb(li + 1)));
+                // ME bracket Bx^2 + ℑxyᶜᶠᵃ(By^2) at cfc(j) and cfc(j+1)
+                auto meb = [&](int b) {
+                    return SQBX(li, b) + avg4(SQBY(li, b - 1), SQBY(li + 1, b - 1), SQBY(li, b), SQBY(li + 1, b));
+                };
+                dg[1] += (0.5 * hh) * (0.5 * (meb(lj) + meb(lj + 1)));
+                const double dh = hh - p.h_ref;
+                dg[2] += (0.5 * p.g) * (dh * dh);
+                dg[3] += hh;
+                dg[4] = fmax(dg[4], fabs(uu));
+                dg[5] = fmax(dg[5], fabs(aa));
+                dg[6] = fmax(dg[6], -hh);
+                {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
+                    const double Amm = RAW(s_A, li - 1, lj - 1), A0m = RAW(s_A, li, lj - 1), Apm = RAW(s_A, li + 1, lj - 1);
+                    const double Am0 = RAW(s_A, li - 1, lj), Ap0 = RAW(s_A, li + 1, lj);
+                    const double Amp = RAW(s_A, li - 1, lj + 1), A0p = RAW(s_A, li, lj + 1), App = RAW(s_A, li + 1, lj + 1);
+                    const double hbx0 = (Amm + A0m) - (Amp + A0p), hbx1 = (A0m + Apm) - (A0p + App);
+                    const double hby0 = (Apm + Ap0) - (Amm + Am0), hby1 = (Ap0 + App) - (Am0 + Amp);
+                    dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
+                }
+                if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) dg[8] += 1.0;
+            }
+        }
+        // fixed-order reduction: R cells per thread (above), warp tree, then the warps in order
+#pragma unroll
+        for (int q = 0; q < NDIAG; q++) {
+            const bool is_max = (q >= 4 && q <= 7);
+            const double x = is_max ? warp_max(dg[q]) : warp_sum(dg[q]);
+            if (lane == 0) s_red[wp * NDIAG + q] = x;
+        }
+        __syncthreads();
+        if (tid < NDIAG) {
+            const bool is_max = (tid >= 4 && tid <= 7);
+            double acc = s_red[tid];
+            for (int w2 = 1; w2 < NW; w2++) { const double x = s_red[w2 * NDIAG + tid]; acc = is_max ? fmax(acc, x) : acc + x; }
+            // partial slots are indexed by 8-row tile rows (the launch granularity of the host side): this
+            // tile fills its first slot and neutral elements into the others it covers
+            const int tr8 = row0 / 8;
+            p.diag[((size_t)tr8 * tiles_x + tile_x) * NDIAG + tid] = acc;
+            for (int s = 1; s < TYB / 8; s++)
+                if (row0 + 8 * s < p.row_end) p.diag[((size_t)(tr8 + s) * tiles_x + tile_x) * NDIAG + tid] = (tid == 6) ? -INFINITY : 0.0;
+        }
+    }
+}
+
+template <int STAGE, bool DIAG>
+cudaError_t launch_rb(const KParams &p, cudaStream_t st) {
+    auto kern = substage_rb_kernel<STAGE, DIAG>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int tiles_x = (p.Nx + TX - 1) / TX;
+    const int tiles_y = (p.row_end - p.row_begin + TYB - 1) / TYB;
+    static int ahead = -1;
+    if (ahead < 0) {
+        int dev = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        const char *env = getenv("SWMHD_RB_AHEAD");
+        ahead = env ? atoi(env) : (occ < 1 ? 1 : occ) * sms;   // CTAs in flight = distance to the slot's next tile
+    }
+    KParams q = p;
+    q.rb_ahead = ahead;
+    kern<<<tiles_x * tiles_y, NT, SMEM_BYTES, st>>>(q);
+    return cudaGetLastError();
+}
+
+} // namespace
+
+void substage_rb_tile(int *tx, int *ty) { *tx = TX; *ty = TYB; }
+
+cudaError_t launch_substage_rb(const KParams &p0, int stage, cudaStream_t st) {
+    if (p0.tile_rows <= 0) return cudaSuccess;
+    if (!p0.use_rb) return cudaErrorInvalidValue;
+    int tx8, ty8;
+    substage_tile(&tx8, &ty8);                              // launch granularity of the host side (tile rows)
+    KParams p = p0;
+    p.row_begin = p0.tile_row0 * ty8;
+    p.row_end = (p0.tile_row0 + p0.tile_rows) * ty8;
+    if (p.row_end > p.Ny) p.row_end = p.Ny;
+    if (p.row_end <= p.row_begin) return cudaSuccess;
+    const bool dg = (p.diag != nullptr);
+    if (dg && stage != 1) return cudaErrorInvalidValue;
+    switch (stage) {
+        case 1: return dg ? launch_rb<1, true>(p, st) : launch_rb<1, false>(p, st);
+        case 2: return launch_rb<2, false>(p, st);
+        case 3: return launch_rb<3, false>(p, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+} // namespace swmhd

@@ -20,7 +20,8 @@ struct swmhd_ctx {
     size_t len[4];
     double *U[2][4];
     CUtensorMap tmap[2][4];     // TMA descriptors of U[b][k]: 2-D (P x rows) FP64, box (TX+6) x (TY+6)
-    int use_tma;
+    CUtensorMap tmap_rb[2][4];  // same arrays, box of the row-blocked kernel
+    int use_tma, use_rb;
     double *G[4];
     int cur;                    // U[cur] = current state
     double *d_partials, *d_diag, *d_stage; // diag partials; d_diag holds NDIAG doubles per slot
@@ -153,6 +154,16 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
         for (int k = 0; k < 4 && ctx->use_tma; k++)
             if (!encode_field_map(&ctx->tmap[b][k], ctx->U[b][k], ctx->P, ctx->rows[k], ctx->tx + 6, ctx->ty + 6)) ctx->use_tma = 0;
     if (getenv("SWMHD_NO_TMA")) ctx->use_tma = 0;
+    // row-blocked kernel (Jacobian form, FAST): taller box; its 8-row launch granularity is ctx->ty
+    ctx->use_rb = (ctx->use_tma && ctx->ty == 8 && c->formulation == SWMHD_JACOBIAN && c->arith == SWMHD_ARITH_FAST) ? 1 : 0;
+    if (ctx->use_rb) {
+        int rtx, rty;
+        substage_rb_tile(&rtx, &rty);
+        for (int b = 0; b < 2 && ctx->use_rb; b++)
+            for (int k = 0; k < 4 && ctx->use_rb; k++)
+                if (!encode_field_map(&ctx->tmap_rb[b][k], ctx->U[b][k], ctx->P, ctx->rows[k], rtx + 6, rty + 6)) ctx->use_rb = 0;
+    }
+    if (getenv("SWMHD_NO_RB")) ctx->use_rb = 0;
     ctx->nblocks_diag = diag_blocks(ctx->Nx, ctx->Ny);
     ctx->ntiles = ((ctx->Nx + ctx->tx - 1) / ctx->tx) * ctx->ntr;
     if (ctx->ntiles > ctx->nblocks_diag) ctx->nblocks_diag = ctx->ntiles;   // d_partials serves both diag paths
@@ -258,6 +269,10 @@ static KParams kparams(swmhd_ctx *ctx, double dt, int stage) {
     p.use_tma = ctx->use_tma;
     if (ctx->use_tma)
         for (int k = 0; k < 4; k++) p.tm[k] = ctx->tmap[ctx->cur][k];
+    p.use_rb = ctx->use_rb;
+    p.row_begin = p.row_end = 0;
+    if (ctx->use_rb)
+        for (int k = 0; k < 4; k++) p.tm_rb[k] = ctx->tmap_rb[ctx->cur][k];
     return p;
 }
 

@@ -12,10 +12,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "ncu launches rc=$?"
 FULL="python bench.py --size 2048 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
 $FULL > gpurun_out/plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:substage_kernel -s 9 -c 3 -f -o gpurun_out/prof_$TAG $FULL > gpurun_out/ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:substage -s 9 -c 3 -f -o gpurun_out/prof_$TAG $FULL > gpurun_out/ncu2.log 2>&1
 echo "ncu full rc=$?"
 FULLD="python bench.py --form divergence --size 2048 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline"
 $FULLD > gpurun_out/plain3.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:substage_kernel -s 9 -c 3 -f -o gpurun_out/prof_div_$TAG $FULLD > gpurun_out/ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:substage -s 9 -c 3 -f -o gpurun_out/prof_div_$TAG $FULLD > gpurun_out/ncu3.log 2>&1
 echo "ncu full div rc=$?"
 ls -la gpurun_out
