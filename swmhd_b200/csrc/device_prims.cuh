@@ -94,4 +94,72 @@ __device__ __forceinline__ void weno_corr4(double d1, double d2, double d3, doub
     den = fma(0.3, a0, fma(0.6, a1, 0.1 * a2));
 }
 
+// ---- batched forms: N independent reconstructions advanced in lock-step ---------------------------
+// The FP64 pipe of an SM sustains its peak only when a warp offers >= 4 independent instructions in a
+// row (tools/micro/fp64_pipe.cu: 2.17 cycles per warp instruction at ILP 4, 3.0 at ILP 1 with any
+// number of warps; dependent-issue latency 8 cycles).  ptxas keeps the source order of independent
+// chains, so the chains are interleaved here, statement by statement.  Arithmetic per chain is that of
+// weno_beta_acc4 / weno_corr4 / frcp.
+#define FORN _Pragma("unroll") for (int n = 0; n < N; n++)
+template <int N>
+__device__ __forceinline__ void beta_acc_n(const double (&d1)[N], const double (&d2)[N], const double (&d3)[N], const double (&d4)[N],
+                                           double (&c0)[N], double (&c1)[N], double (&c2)[N]) {
+    constexpr double r = 3.0 / 13.0;
+    double D0[N], E0[N], D1[N], E1[N], D2[N], E2[N];
+    FORN D0[n] = d4[n] - d3[n];
+    FORN E0[n] = fma(-3.0, d3[n], d4[n]);
+    FORN D1[n] = d3[n] - d2[n];
+    FORN E1[n] = d2[n] + d3[n];
+    FORN D2[n] = d2[n] - d1[n];
+    FORN E2[n] = fma(3.0, d2[n], -d1[n]);
+    double t0[N], t1[N], t2[N];
+    FORN t0[n] = r * E0[n];
+    FORN t1[n] = r * E1[n];
+    FORN t2[n] = r * E2[n];
+    FORN t0[n] = fma(t0[n], E0[n], c0[n]);
+    FORN t1[n] = fma(t1[n], E1[n], c1[n]);
+    FORN t2[n] = fma(t2[n], E2[n], c2[n]);
+    FORN c0[n] = fma(D0[n], D0[n], t0[n]);
+    FORN c1[n] = fma(D1[n], D1[n], t1[n]);
+    FORN c2[n] = fma(D2[n], D2[n], t2[n]);
+}
+template <int N>
+__device__ __forceinline__ void corr_n(const double (&d1)[N], const double (&d2)[N], const double (&d3)[N], const double (&d4)[N],
+                                       const double (&c0)[N], const double (&c1)[N], const double (&c2)[N],
+                                       double (&num)[N], double (&den)[N]) {
+    double tau[N], s0[N], s1[N], s2[N], q0[N], q1[N], q2[N], S[N], Y0[N], Y1[N], Y2[N];
+    FORN tau[n] = c2[n] - c0[n];
+    FORN s0[n] = c0[n] * c0[n];
+    FORN s1[n] = c1[n] * c1[n];
+    FORN s2[n] = c2[n] * c2[n];
+    FORN Y0[n] = -0.05 * d4[n];
+    FORN Y1[n] = 0.1 * d2[n];
+    FORN Y2[n] = (-1.0 / 30.0) * d1[n];
+    FORN tau[n] = tau[n] * tau[n];
+    FORN q2[n] = s0[n] * s1[n];
+    FORN q0[n] = s1[n] * s2[n];
+    FORN q1[n] = s0[n] * s2[n];
+    FORN Y0[n] = fma(0.2, d3[n], Y0[n]);                         // 0.3/6 (4 d3 - d4)
+    FORN Y1[n] = fma(0.2, d3[n], Y1[n]);                         // 0.6/6 (d2 + 2 d3)
+    FORN Y2[n] = fma(1.0 / 12.0, d2[n], Y2[n]);                  // 0.1/6 (5 d2 - 2 d1)
+    FORN S[n] = q2[n] * s2[n];
+    FORN q0[n] = fma(tau[n], q0[n], S[n]);                       // a0
+    FORN q1[n] = fma(tau[n], q1[n], S[n]);                       // a1
+    FORN q2[n] = fma(tau[n], q2[n], S[n]);                       // a2
+    FORN num[n] = q2[n] * Y2[n];
+    FORN den[n] = 0.1 * q2[n];
+    FORN num[n] = fma(q1[n], Y1[n], num[n]);
+    FORN den[n] = fma(0.6, q1[n], den[n]);
+    FORN num[n] = fma(q0[n], Y0[n], num[n]);
+    FORN den[n] = fma(0.3, q0[n], den[n]);
+}
+template <int N>
+__device__ __forceinline__ void rcp_n(const double (&x)[N], double (&r)[N]) {
+    double e[N];
+    FORN asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[n]) : "d"(x[n]));
+    FORN e[n] = fma(-x[n], r[n], 1.0);
+    FORN r[n] = fma(r[n], e[n], r[n]);
+    FORN e[n] = fma(-x[n], r[n], 1.0);
+    FORN r[n] = fma(r[n], e[n], r[n]);
+}
 } // namespace swmhd
