@@ -50,11 +50,7 @@ constexpr int CP = TX + 2, CR = TYB + 2;                   // ccc points a in [2
 constexpr int NZ = ZP * ZR, NC = CP * CR;
 constexpr int o_z = 0, o_ut = NZ, o_vt = 2 * NZ, o_K = 3 * NZ, o_Bx = o_K + NC, o_By = o_Bx + NC;
 constexpr int DERIVED = o_By + NC;
-// DIAG: squared face B fields, aliased onto the (dead) zeta arrays
-constexpr int QXP = TX, QXR = TYB + 1;                     // (dyA/ℑy h)^2 at cfc: a in [3,TX+2], b in [3,TYB+3]
-constexpr int QYP = TX + 1, QYR = TYB + 2;                 // (dxA/ℑx h)^2 at fcc: a in [3,TX+3], b in [2,TYB+3]
-static_assert(QXP * QXR + QYP * QYR + NW * NDIAG <= 3 * NZ, "diag scratch must fit in the zeta arrays");
-constexpr size_t SMEM_BYTES = ((size_t)4 * SZP + DERIVED) * sizeof(double) + 16;
+constexpr size_t SMEM_BYTES = ((size_t)4 * SZP + DERIVED + 2 + NW * NDIAG) * sizeof(double);   // + mbarrier + DIAG partials
 
 #define RAW(arr, a, b) arr[(b) * W + (a)]
 #define Zf(arr, a, b) arr[((b) - 1) * ZP + (a) - 1]
@@ -356,53 +352,89 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     }
 
     // ---- fused diagnostics of the state at the start of the step --------------------------
+    // Warp-private like the rest: every thread evaluates the squared face fields of its own column for
+    // its R cells from the raw tile (2R+3 reciprocals advanced together), the east neighbours come by
+    // shuffle, the tile's east column from lanes 0..R+1.
     if constexpr (DIAG) {
-        double *const s_sqBx = smem, *const s_sqBy = smem + QXP * QXR, *const s_red = s_sqBy + QYP * QYR;
-        __syncthreads();                                    // every warp is done with the zeta arrays
-        for (int q = tid; q < QXP * QXR; q += NT) {          // (dyA / ℑy h)^2 at cfc
-            const int a = 3 + q % QXP, b = 3 + q / QXP;
-            const double bx = -((RAW(s_A, a, b) - RAW(s_A, a, b - 1)) * p.rdy) * frcp(0.5 * (RAW(s_h, a, b - 1) + RAW(s_h, a, b)));
-            s_sqBx[q] = bx * bx;
-        }
-        for (int q = tid; q < QYP * QYR; q += NT) {          // (dxA / ℑx h)^2 at fcc
-            const int a = 3 + q % QYP, b = 2 + q / QYP;
-            const double by_ = ((RAW(s_A, a, b) - RAW(s_A, a - 1, b)) * p.rdx) * frcp(0.5 * (RAW(s_h, a - 1, b) + RAW(s_h, a, b)));
-            s_sqBy[q] = by_ * by_;
-        }
-        __syncthreads();
+        double *const s_red = smem + DERIVED + 2;            // NW x NDIAG partials (behind the mbarrier word)
+        constexpr int NR = R + 2;                            // rows b = lj0-1 .. lj0+R, index k = b - (lj0-1)
         auto sq = [](double x) { return x * x; };
-        auto SQBX = [&](int a, int b) { return s_sqBx[(b - 3) * QXP + a - 3]; };
-        auto SQBY = [&](int a, int b) { return s_sqBy[(b - 2) * QYP + a - 3]; };
+        double Ac[NR], Aw[NR], Ae[NR], hcol[NR], sqy[NR], sqx[NR];
+        {
+            double den[2 * NR - 1], rc[2 * NR - 1], hwst[NR];
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+                const int b = lj0 - 1 + k;
+                Ac[k] = RAW(s_A, li, b); Aw[k] = RAW(s_A, li - 1, b); Ae[k] = RAW(s_A, li + 1, b);
+                hcol[k] = RAW(s_h, li, b); hwst[k] = RAW(s_h, li - 1, b);
+            }
+#pragma unroll
+            for (int k = 0; k < NR; k++) den[k] = 0.5 * (hwst[k] + hcol[k]);                 // ℑx h at fcc(li, b)
+#pragma unroll
+            for (int k = 1; k < NR; k++) den[NR + k - 1] = 0.5 * (hcol[k - 1] + hcol[k]);     // ℑy h at cfc(li, b)
+            rcp_n<2 * NR - 1>(den, rc);
+#pragma unroll
+            for (int k = 0; k < NR; k++) sqy[k] = sq(((Ac[k] - Aw[k]) * p.rdx) * rc[k]);      // (dxA / ℑx h)^2
+            sqx[0] = 0.0;
+#pragma unroll
+            for (int k = 1; k < NR; k++) sqx[k] = sq(-((Ac[k] - Ac[k - 1]) * p.rdy) * rc[NR + k - 1]);   // (dyA / ℑy h)^2
+        }
+        double uu[R], vc[R + 1], kb[R];
+        {
+            double vw2[R + 1], vc2[R + 1];
+#pragma unroll
+            for (int k = 0; k <= R; k++) { vc[k] = RAW(s_v, li, lj0 + k); vc2[k] = sq(vc[k]); vw2[k] = sq(RAW(s_v, li - 1, lj0 + k)); }
+#pragma unroll
+            for (int r = 0; r < R; r++) {                    // KE bracket u^2 + ℑxyᶠᶜᵃ(v^2) at fcc(li)
+                uu[r] = RAW(s_u, li, lj0 + r);
+                kb[r] = sq(uu[r]) + avg4(vw2[r], vc2[r], vw2[r + 1], vc2[r + 1]);
+            }
+        }
+        // the tile's east column (a = TX+3), lane l takes row k = l
+        double e_sqy = 0.0, e_kb = 0.0;
+        if (lane < NR) {
+            const int b = lj0 - 1 + lane, a = TX + 3;
+            e_sqy = sq(((RAW(s_A, a, b) - RAW(s_A, a - 1, b)) * p.rdx) * frcp(0.5 * (RAW(s_h, a - 1, b) + RAW(s_h, a, b))));
+            if (lane < R) {
+                const int bb = lj0 + lane;
+                e_kb = sq(RAW(s_u, a, bb)) + avg4(sq(RAW(s_v, a - 1, bb)), sq(RAW(s_v, a, bb)), sq(RAW(s_v, a - 1, bb + 1)), sq(RAW(s_v, a, bb + 1)));
+            }
+        }
+        double sqye[NR], kbe[R];
+#pragma unroll
+        for (int k = 0; k < NR; k++) {
+            sqye[k] = __shfl_down_sync(0xffffffffu, sqy[k], 1);
+            const double t = __shfl_sync(0xffffffffu, e_sqy, k);
+            if (lane == 31) sqye[k] = t;
+        }
 #pragma unroll
         for (int r = 0; r < R; r++) {
-            const int lj = lj0 + r, j = jc0 + r;
+            kbe[r] = __shfl_down_sync(0xffffffffu, kb[r], 1);
+            const double t = __shfl_sync(0xffffffffu, e_kb, r);
+            if (lane == 31) kbe[r] = t;
+        }
+        double mb[R + 1];                                    // ME bracket Bx^2 + ℑxyᶜᶠᵃ(By^2) at cfc(li, b), b = lj0 .. lj0+R
+#pragma unroll
+        for (int k = 1; k < NR; k++) mb[k - 1] = sqx[k] + avg4(sqy[k - 1], sqye[k - 1], sqy[k], sqye[k]);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int j = jc0 + r, k = r + 1;
             if ((i <= Nx) && (j <= p.row_end)) {
-                const double hh = RAW(s_h, li, lj), aa = RAW(s_A, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj);
-                // KE bracket u^2 + ℑxyᶠᶜᵃ(v^2) at fcc(i) and fcc(i+1), averaged to the centre
-                auto keb = [&](int a) {
-                    return sq(RAW(s_u, a, lj)) + avg4(sq(RAW(s_v, a - 1, lj)), sq(RAW(s_v, a, lj)), sq(RAW(s_v, a - 1, lj + 1)), sq(RAW(s_v, a, lj + 1)));
-                };
-                dg[0] += (0.5 * hh) * (0.5 * (keb(li) + keb(li + 1)));
-                // ME bracket Bx^2 + ℑxyᶜᶠᵃ(By^2) at cfc(j) and cfc(j+1)
-                auto meb = [&](int b) {
-                    return SQBX(li, b) + avg4(SQBY(li, b - 1), SQBY(li + 1, b - 1), SQBY(li, b), SQBY(li + 1, b));
-                };
-                dg[1] += (0.5 * hh) * (0.5 * (meb(lj) + meb(lj + 1)));
+                const double hh = hcol[k], aa = Ac[k];
+                dg[0] += (0.5 * hh) * (0.5 * (kb[r] + kbe[r]));
+                dg[1] += (0.5 * hh) * (0.5 * (mb[r] + mb[r + 1]));
                 const double dh = hh - p.h_ref;
                 dg[2] += (0.5 * p.g) * (dh * dh);
                 dg[3] += hh;
-                dg[4] = fmax(dg[4], fabs(uu));
+                dg[4] = fmax(dg[4], fabs(uu[r]));
                 dg[5] = fmax(dg[5], fabs(aa));
                 dg[6] = fmax(dg[6], -hh);
                 {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
-                    const double Amm = RAW(s_A, li - 1, lj - 1), A0m = RAW(s_A, li, lj - 1), Apm = RAW(s_A, li + 1, lj - 1);
-                    const double Am0 = RAW(s_A, li - 1, lj), Ap0 = RAW(s_A, li + 1, lj);
-                    const double Amp = RAW(s_A, li - 1, lj + 1), A0p = RAW(s_A, li, lj + 1), App = RAW(s_A, li + 1, lj + 1);
-                    const double hbx0 = (Amm + A0m) - (Amp + A0p), hbx1 = (A0m + Apm) - (A0p + App);
-                    const double hby0 = (Apm + Ap0) - (Amm + Am0), hby1 = (Ap0 + App) - (Am0 + Amp);
+                    const double hbx0 = (Aw[k - 1] + Ac[k - 1]) - (Aw[k + 1] + Ac[k + 1]), hbx1 = (Ac[k - 1] + Ae[k - 1]) - (Ac[k + 1] + Ae[k + 1]);
+                    const double hby0 = (Ae[k - 1] + Ae[k]) - (Aw[k - 1] + Aw[k]), hby1 = (Ae[k] + Ae[k + 1]) - (Aw[k] + Aw[k + 1]);
                     dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
                 }
-                if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) dg[8] += 1.0;
+                if (!(isfinite(hh) && isfinite(aa) && isfinite(uu[r]) && isfinite(vc[r]))) dg[8] += 1.0;
             }
         }
         // fixed-order reduction: R cells per thread (above), warp tree, then the warps in order
