@@ -249,7 +249,8 @@ def run_native(args):
         launches = ctx.launch_count - l0
         torch.cuda.synchronize()
         # dominant kernel, live: event pair around every fused substage launch
-        st_ms = ctx.step_profile(dt, min(K, 20))
+        st_ms = ctx.step_profile(dt, min(K, 20), diag=True)      # the launches of the timed region (stage 1 with diagnostics)
+        st_ms_plain = ctx.step_profile(dt, min(K, 20))
         clocks = sampler.stop() if sampler else None
         ncell = Nx * NyG
         peak, peak_src = hbm_peak()
@@ -259,9 +260,10 @@ def run_native(args):
         achieved = mean_bytes / (mean_ms * 1e-3) / 1e9
         traffic = ncu_traffic(args.form, ncell)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "swmhd::substage_kernel<FORM,STAGE>",
+                "traffic": traffic, "peak_source": peak_src, "kernel": ("swmhd::substage_rb_kernel<1,DIAG> (stage 1) + swmhd::substage_kernel<0,STAGE> (stages 2, 3)"
+                           if form == abi.JACOBIAN and arith == abi.ARITH_FAST else "swmhd::substage_kernel<FORM,STAGE>"),
                 "bytes_per_launch": mean_bytes, "ms_per_launch": mean_ms,
-                "per_stage": {"ms": st_ms, "GB/s": ach},
+                "per_stage": {"ms": st_ms, "GB/s": ach, "ms_without_diagnostics": st_ms_plain},
                 "second_ceiling": "FP64 issue: 148 SM x 64 lanes; see DESIGN.md (the kernel is FP64-pipe bound, not HBM bound)"}
         finite = all(d["all_finite"] for d in diags)
         # ---- end to end through the public API with host buffers -------------------------

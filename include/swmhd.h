@@ -180,6 +180,8 @@ int  swmhd_get_diag_slots(swmhd_ctx *ctx, int first, int count, swmhd_diag *out)
 /* nsteps RK3 steps with a CUDA-event pair around every fused substage-kernel launch;
    out_ms[s] = mean device time of the stage-(s+1) kernel (roofline measurement). */
 int  swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]);
+/* same with the diagnostics fused into every stage-1 launch (what swmhd_step_diag runs) */
+int  swmhd_step_profile_diag(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]);
 int64_t swmhd_launch_count(const swmhd_ctx *ctx);
 double  swmhd_last_step_ms(const swmhd_ctx *ctx);
 

@@ -106,6 +106,7 @@ SYMBOLS = [
     ("swmhd_arm_diag", C.c_int, [_ctx, C.c_int]),
     ("swmhd_get_diag_slots", C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(Diag)]),
     ("swmhd_step_profile", C.c_int, [_ctx, C.c_double, C.c_int, C.POINTER(C.c_double)]),
+    ("swmhd_step_profile_diag", C.c_int, [_ctx, C.c_double, C.c_int, C.POINTER(C.c_double)]),
     ("swmhd_launch_count", C.c_int64, [_ctx]),
     ("swmhd_last_step_ms", C.c_double, [_ctx]),
 ]

@@ -87,10 +87,12 @@ class Context:
         self._ck(self.lib.swmhd_step_diag(self._h, float(dt), int(nsteps), arr))
         return [d.as_dict() for d in arr]
 
-    def step_profile(self, dt, nsteps=1):
-        """Mean device time (ms) of the three fused substage kernels over nsteps steps."""
+    def step_profile(self, dt, nsteps=1, diag=False):
+        """Mean device time (ms) of the three fused substage kernels over nsteps steps
+        (diag=True: with the diagnostics fused into stage 1, as step_diag runs them)."""
         out = (C.c_double * 3)()
-        self._ck(self.lib.swmhd_step_profile(self._h, float(dt), int(nsteps), out))
+        fn = self.lib.swmhd_step_profile_diag if diag else self.lib.swmhd_step_profile
+        self._ck(fn(self._h, float(dt), int(nsteps), out))
         return list(out)
 
     def substage(self, dt, stage):

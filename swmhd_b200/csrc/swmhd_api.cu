@@ -401,7 +401,10 @@ extern "C" int swmhd_step_diag(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag
 
 // nsteps RK3 steps with a CUDA-event pair around every substage-kernel launch (on the
 // launching stream); out_ms[s] = mean device duration of the stage-(s+1) kernel.
-extern "C" int swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) {
+static int step_profile_impl(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3], bool with_diag);
+extern "C" int swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) { return step_profile_impl(ctx, dt, nsteps, out_ms, false); }
+extern "C" int swmhd_step_profile_diag(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) { return step_profile_impl(ctx, dt, nsteps, out_ms, true); }
+static int step_profile_impl(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3], bool with_diag) {
     if (!ctx || !out_ms) return SWMHD_ERR_ARG;
     if (nsteps < 1 || nsteps > 512) return fail(ctx, SWMHD_ERR_ARG, "nsteps must be in 1..512");
     if (ctx->cfg.world != 1) return fail(ctx, SWMHD_ERR_STATE, "single-slab only");
@@ -411,7 +414,7 @@ extern "C" int swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double 
     int rc = SWMHD_OK;
     for (int n = 0; n < nsteps && rc == SWMHD_OK; n++)
         for (int s = 1; s <= 3 && rc == SWMHD_OK; s++)
-            rc = substage_async(ctx, dt, s, ev[(size_t)n * 6 + 2 * (s - 1)], ev[(size_t)n * 6 + 2 * (s - 1) + 1]);
+            rc = substage_async(ctx, dt, s, ev[(size_t)n * 6 + 2 * (s - 1)], ev[(size_t)n * 6 + 2 * (s - 1) + 1], with_diag ? (n % ctx->diag_slots) : -1);
     if (rc == SWMHD_OK) {
         CK(cudaStreamSynchronize(ctx->main));
         for (int s = 0; s < 3; s++) {

@@ -284,3 +284,20 @@ def test_fuzz_strict_bit_identity():
         O.step(cfg, U, dt, nst)
         for k in range(4):
             assert np.array_equal(Ug[k], U[k]), (trial, kind, N, Ny, seed, nst, k)
+
+
+@pytest.mark.parametrize("kind", ["J", "D"])
+def test_step_profile_variants_advance_like_step(kind):
+    """swmhd_step_profile / swmhd_step_profile_diag (measurement entry points) run the same launches as swmhd_step."""
+    g, cfg, U = make_case(kind, 96, arith=abi.ARITH_FAST, perturb=5)
+    ref = run_gpu(cfg, [u.copy() for u in U], 0.004, 3)
+    for diag in (False, True):
+        ctx = Context(cfg)
+        ctx.set_state([u.copy() for u in U])
+        ctx.fill_halos()
+        ms = ctx.step_profile(0.004, 3, diag=diag)
+        out = ctx.get_state()
+        ctx.close()
+        assert len(ms) == 3 and all(m > 0 for m in ms)
+        for k in range(4):
+            assert np.array_equal(out[k], ref[k])
