@@ -28,7 +28,7 @@ struct KParams {
     int use_tma;         // 1: tm[] are valid tensor maps of Uo[] (TMA tile loads)
     alignas(64) CUtensorMap tm[4];
     int use_rb;          // 1: tm_rb[] are valid (row-blocked kernel, substage_rb.cu: taller TMA box)
-    int rb_ahead;        // L2 prefetch distance in tiles (CTAs in flight)
+    int l2_ahead;        // L2 prefetch distance in tiles (CTAs in flight)
     int row_begin, row_end;   // 0-based cell rows [row_begin, row_end) of this launch (set by the rb launcher)
     alignas(64) CUtensorMap tm_rb[4];
     double *diag;        // per-CTA diagnostic partials [tiles][NDIAG] (stage-1 DIAG variant), or nullptr

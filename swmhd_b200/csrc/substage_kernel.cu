@@ -271,6 +271,18 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
     if constexpr (TMA && NSTG == 2) {
         if (tid == 0 && tile_lo < tile_hi) issue_load(tile_lo, 0);
     }
+    if constexpr (TMA) {
+        // pull the first tile of the CTA that will take over this slot into L2 now (CTAs are dispatched in
+        // blockIdx order): its TMA wait then costs an L2 hit instead of an HBM round trip
+        if (tid == 0 && p.l2_ahead > 0) {
+            const int nxt = (blockIdx.x + p.l2_ahead) * tpc;
+            if (nxt < ntiles) {
+                const int c0 = (nxt % tiles_x) * TX, c1 = (p.tile_row0 + nxt / tiles_x) * TY;
+#pragma unroll
+                for (int k = 0; k < 4; k++) tma_prefetch_2d(&p.tm[k], c0, c1);
+            }
+        }
+    }
 
     // own cell of this thread (tile-local)
     const int tx = tid % TX, ty = tid / TX;
@@ -865,7 +877,9 @@ cudaError_t launch_cfg(const KParams &p, cudaStream_t st) {
     KParams q = p;
     q.tiles_per_cta = (NSTG == 2) ? tpc : 1;
     const int grid = (ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
-    (void)max_ctas;
+    static int ahead = -2;
+    if (ahead == -2) { const char *e = getenv("SWMHD_L2_AHEAD"); ahead = e ? atoi(e) : -1; }
+    q.l2_ahead = (ahead >= 0) ? ahead : max_ctas;               // CTAs in flight = distance to the slot's next CTA
     kern<<<grid, NT, bytes, st>>>(q);
     return cudaGetLastError();
 }

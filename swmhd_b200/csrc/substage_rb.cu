@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
 #if RB_L2_PREFETCH
         // pull the tile that the CTA taking over this slot will load into L2 now (CTAs are dispatched in
         // blockIdx order): its TMA wait then costs an L2 hit instead of an HBM round trip
-        const int nxt = blockIdx.x + p.rb_ahead;
+        const int nxt = blockIdx.x + p.l2_ahead;
         if (nxt < gridDim.x) {
 #pragma unroll
             for (int k = 0; k < 4; k++) tma_prefetch_2d(&p.tm_rb[k], (nxt % tiles_x) * TX, p.row_begin + (nxt / tiles_x) * TYB);
@@ -477,11 +477,11 @@ cudaError_t launch_rb(const KParams &p, cudaStream_t st) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        const char *env = getenv("SWMHD_RB_AHEAD");
+        const char *env = getenv("SWMHD_L2_AHEAD");
         ahead = env ? atoi(env) : (occ < 1 ? 1 : occ) * sms;   // CTAs in flight = distance to the slot's next tile
     }
     KParams q = p;
-    q.rb_ahead = ahead;
+    q.l2_ahead = ahead;
     kern<<<tiles_x * tiles_y, NT, SMEM_BYTES, st>>>(q);
     return cudaGetLastError();
 }
