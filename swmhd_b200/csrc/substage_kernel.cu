@@ -895,12 +895,11 @@ cudaError_t LAUNCH_NAME(const KParams &p, int form, int stage, cudaStream_t st) 
     const bool dg = (p.diag != nullptr);
     if (dg && stage != 1) return cudaErrorInvalidValue;
 #if !SWMHD_STRICT
-    // Jacobian form with TMA: the row-blocked kernel (substage_rb.cu) for the stages in the mask
-    // (bit s-1 = stage s).  Measured at 4096^2: stage 1 0.736 vs 0.761 ms (and its DIAG variant 0.97 vs
-    // 1.06 ms), stage 2 equal, stage 3 0.785 vs 0.746 ms — default: stage 1 only.
+    // Jacobian form with TMA: the row-blocked kernel (substage_rb.cu); SWMHD_RB_STAGES masks stages
+    // (bit s-1 = stage s, default 7 = all) for A/B runs against this file's kernel.
     if (form == 0 && stage >= 1 && p.use_tma && p.use_rb) {
         static int mask = -1;
-        if (mask < 0) { const char *e = getenv("SWMHD_RB_STAGES"); mask = e ? atoi(e) : 1; }
+        if (mask < 0) { const char *e = getenv("SWMHD_RB_STAGES"); mask = e ? atoi(e) : 7; }
         if ((mask >> (stage - 1)) & 1) return launch_substage_rb(p, stage, st);
     }
 #endif

@@ -4,20 +4,19 @@
 // for all four fields, jacobian_formulation/sw_mhd_jacobian_functions.jl:1-26 inlined; in the
 // stage-1 DIAG variant also the diagnostics of SWMHD_example.jl:47-77), different thread mapping:
 //
-//   * a CTA owns a 32 x RB_TY tile, a WARP owns RB_R consecutive rows of it, a THREAD one column of
-//     those rows (RB_R cells).  Everything differenced or reconstructed along y (the vorticity
-//     reconstruction with its two velocity-stencil smoothness fields, the h and A fluxes through the
-//     y faces) is fed from a register window of the thread's column: (R+5)/R shared-memory loads per
-//     cell and stencil instead of 5, first differences shared between neighbouring faces.
-//   * the upwind side of a register window is chosen by SELECTING mirrored first differences
-//     (the smoothness indicators are even, the correction is odd in them), bit-identical to
-//     reconstructing the mirrored samples.
-//   * after the derived staggered fields (phase A, CTA-wide) warps never meet again: the east-face
-//     fluxes travel by warp shuffle, the tile's east column of faces is a per-warp pre-pass, every
-//     warp evaluates its own north face.  One __syncthreads per tile (three more in the DIAG variant).
+//   * a CTA owns a 32 x RB_TY tile staged by TMA, a WARP owns RB_R consecutive rows of it and walks
+//     them south to north, a THREAD one column of those rows.
+//   * after the derived staggered fields (phase A, CTA-wide) warps never meet again: the flux through
+//     a cell's north face is kept in registers for the next row (one extra evaluation per warp for the
+//     south face of its first row), the east-face fluxes travel by warp shuffle, the tile's east column
+//     of faces is a per-warp pre-pass.  One __syncthreads per tile (one more in the DIAG variant)
+//     instead of three, and no flux arrays in shared memory.
+//   * the next tile of the SM slot is pulled into L2 while this one computes (cp.async.bulk.prefetch).
 //
-// The shared-memory operand traffic drops from ~138 to ~85 accesses per cell-substage, which is what
-// bound the one-thread-per-cell kernel together with the FP64 pipe (profiles/README.md).
+// Measured (profiles/README.md): 0.714 / 0.752 / 0.726 ms per stage at 4096^2 against 0.756 / 0.782 /
+// 0.743 ms of the one-thread-per-cell kernel; with the fused diagnostics 0.87 vs 1.06 ms.  A variant
+// that also kept the y stencils in sliding register windows was slower (register moves and selects
+// outweighed the saved shared-memory loads): see the history table there.
 // Arithmetic per value is the FAST arithmetic of substage_kernel.cu (same operation order).
 #include "kparams.h"
 #include "device_prims.cuh"
@@ -75,31 +74,6 @@ __device__ __forceinline__ double upwind_weno_mem(const double *ctr, double vel,
     const bool pos = vel > 0.0;
     return vel * weno5_mem(pos ? ctr - 3 : ctr + 2, pos ? 1 : -1, eps * (12.0 / 13.0));
 }
-// ---- WENO5-Z from a sliding register window (y direction) -------------------------------------------
-// The window holds psi[f-3..f+2] = q0..q5 along the thread's column as first differences
-// D[k] = q[k+1]-q[k] plus the samples q2..q5.  Left-biased (pos): samples q0..q4, differences
-// (D0,D1,D2,D3), centre q2.  Right-biased: samples q5..q1, whose differences are -(D4,D3,D2,D1),
-// centre q3: the indicators are even in the differences, the correction is odd — selecting the
-// differences is bit-identical to reconstructing the mirrored samples.
-struct Win { double q2, q3, q4, q5, D0, D1, D2, D3, D4; };
-struct WinD { double last, D0, D1, D2, D3, D4; };           // smoothness-only field: differences + newest sample
-__device__ __forceinline__ void win_load(Win &w, const double *p0, int st) {   // p0 = &psi[f-3]
-    const double q0 = p0[0], q1 = p0[st];
-    w.q2 = p0[2 * st]; w.q3 = p0[3 * st]; w.q4 = p0[4 * st]; w.q5 = p0[5 * st];
-    w.D0 = q1 - q0; w.D1 = w.q2 - q1; w.D2 = w.q3 - w.q2; w.D3 = w.q4 - w.q3; w.D4 = w.q5 - w.q4;
-}
-__device__ __forceinline__ void win_load(WinD &w, const double *p0, int st) {
-    const double q0 = p0[0], q1 = p0[st], q2 = p0[2 * st], q3 = p0[3 * st], q4 = p0[4 * st];
-    w.last = p0[5 * st];
-    w.D0 = q1 - q0; w.D1 = q2 - q1; w.D2 = q3 - q2; w.D3 = q4 - q3; w.D4 = w.last - q4;
-}
-__device__ __forceinline__ void win_push(Win &w, double n) {                   // f -> f+1
-    w.D0 = w.D1; w.D1 = w.D2; w.D2 = w.D3; w.D3 = w.D4; w.D4 = n - w.q5;
-    w.q2 = w.q3; w.q3 = w.q4; w.q4 = w.q5; w.q5 = n;
-}
-__device__ __forceinline__ void win_push(WinD &w, double n) {
-    w.D0 = w.D1; w.D1 = w.D2; w.D2 = w.D3; w.D3 = w.D4; w.D4 = n - w.last; w.last = n;
-}
 // first differences of the five upwind samples of a shared-memory line (pointer-selected side)
 __device__ __forceinline__ void diffs_mem(const double *q, int s, double &d1, double &d2, double &d3, double &d4, double &c) {
     const double a = q[0], b = q[s], e = q[4 * s], d = q[3 * s];
@@ -109,7 +83,9 @@ __device__ __forceinline__ void diffs_mem(const double *q, int s, double &d1, do
 __device__ __forceinline__ void diffs_mem(const double *q, int s, double &d1, double &d2, double &d3, double &d4) {
     double c; diffs_mem(q, s, d1, d2, d3, d4, c);
 }
-#define SELW(pos, w, n) d1[n] = (pos) ? (w).D0 : (w).D4; d2[n] = (pos) ? (w).D1 : (w).D3; d3[n] = (w).D2; d4[n] = (pos) ? (w).D3 : (w).D1
+// stencil of face f along a line of stride st (ctr = &psi[f]): left-biased psi[f-3..f+1] for pos, else the mirror
+#define UPD(pos, ctr, st, n) diffs_mem((pos) ? (ctr) - 3 * (st) : (ctr) + 2 * (st), (pos) ? (st) : -(st), d1[n], d2[n], d3[n], d4[n])
+#define UPDC(pos, ctr, st, n, cvar) diffs_mem((pos) ? (ctr) - 3 * (st) : (ctr) + 2 * (st), (pos) ? (st) : -(st), d1[n], d2[n], d3[n], d4[n], cvar)
 
 // STAGE 1,2,3.  DIAG only with STAGE 1.
 template <int STAGE, bool DIAG>
@@ -191,17 +167,8 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
         eastF = upwind_weno_mem(&RAW(arr, TX + 3, b), RAW(s_u, TX + 3, b), eps);
     }
 
-    // Sliding windows along the own column: rows lj-2 .. lj+3 around the current row lj.  They feed the
-    // vorticity reconstruction to the centre of row lj (faces lj-2..lj+3) and the h, A fluxes through
-    // the NORTH face lj+1 of that row (samples lj-2..lj+3).  Iteration it = -1 only produces the south
-    // face of the warp's first row.
-    Win wz, wh, wA;
-    WinD wu, wv;
-    win_load(wz, &Zf(s_z, li, lj0 - 3), ZP);     // (row lj0-3 of warp 0 lies outside the zeta arrays: it is read from
-    win_load(wu, &Zf(s_ut, li, lj0 - 3), ZP);    //  valid shared memory and shifted out before the window is used)
-    win_load(wv, &Zf(s_vt, li, lj0 - 3), ZP);
-    win_load(wh, &RAW(s_h, li, lj0 - 3), W);
-    win_load(wA, &RAW(s_A, li, lj0 - 3), W);
+    // Row loop.  Iteration it = -1 only produces the fluxes through the south face of the warp's first
+    // row; every other iteration evaluates the NORTH face lj+1 of its row and keeps it for the next one.
     double vC = RAW(s_v, li, lj0 - 1), vW = RAW(s_v, li - 1, lj0 - 1);
     double fyh_s = 0.0, fyA_s = 0.0;
     double dg[NDIAG];
@@ -230,17 +197,19 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
         const bool posN = vN > 0.0, bufN = ybuf(p.by, gj + 1, 3, p.NyG);
         const double es1 = eps * (12.0 / 13.0), es2 = eps * (24.0 / 13.0);
         double fyh_n, fyA_n;
+        const double *const ph = &RAW(s_h, li, lj + 1), *const pA = &RAW(s_A, li, lj + 1);   // north face lj+1
         if (it < 0) {
-            // south face of the warp's first row: h and A fluxes from the windows
+            // south face of the warp's first row: h and A fluxes
             double d1[2], d2[2], d3[2], d4[2], c0[2] = {es1, es1}, c1[2] = {es1, es1}, c2[2] = {es1, es1}, num[2], den[2], rc[2];
-            SELW(posN, wh, 0); SELW(posN, wA, 1);
+            double ch, cA;
+            UPDC(posN, ph, W, 0, ch); UPDC(posN, pA, W, 1, cA);
             beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
             corr_n<2>(d1, d2, d3, d4, c0, c1, c2, num, den);
             rcp_n<2>(den, rc);
-            const double wh_ = vN * fma(posN ? num[0] : -num[0], rc[0], posN ? wh.q2 : wh.q3);
-            const double wA_ = vN * fma(posN ? num[1] : -num[1], rc[1], posN ? wA.q2 : wA.q3);
-            fyh_n = bufN ? vN * sym2(wh.q2, wh.q3) : wh_;
-            fyA_n = bufN ? vN * sym2(wA.q2, wA.q3) : wA_;
+            const double wh_ = vN * fma(num[0], rc[0], ch);
+            const double wA_ = vN * fma(num[1], rc[1], cA);
+            fyh_n = bufN ? vN * sym2(ph[-W], ph[0]) : wh_;
+            fyA_n = bufN ? vN * sym2(pA[-W], pA[0]) : wA_;
         } else {
             const double vhat = avg4(vW, vC, vWn, vN);
             const double uw = RAW(s_u, li, lj), ue = RAW(s_u, li + 1, lj);
@@ -251,28 +220,29 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
             const double *qh = posx ? &RAW(s_h, li - 3, lj) : &RAW(s_h, li + 2, lj);
             const double *qA = posx ? &RAW(s_A, li - 3, lj) : &RAW(s_A, li + 2, lj);
             const int sp = posx ? 1 : -1;
-            double rc[8], num2[2], num4[4], cz1, ch2, cA3;
-            {   // vorticity pair: [0] to the centre of row lj along y (windows), [1] to the centre i along x (memory);
+            const double *const pz = &Zf(s_z, li, lj + 1), *const pu = &Zf(s_ut, li, lj + 1), *const pv = &Zf(s_vt, li, lj + 1);
+            double rc[8], num2[2], num4[4], cz0, cz1, ch0, cA1, ch2, cA3;
+            {   // vorticity pair: [0] to the centre of row lj along y, [1] to the centre i along x;
                 // VelocityStencil smoothness: beta accumulated over ℑy u and ℑx v
                 double d1[2], d2[2], d3[2], d4[2], c0[2] = {es2, es2}, c1[2] = {es2, es2}, c2[2] = {es2, es2}, den[2];
-                SELW(posv, wu, 0); diffs_mem(s_ut + offx, sx, d1[1], d2[1], d3[1], d4[1]);
+                UPD(posv, pu, ZP, 0); diffs_mem(s_ut + offx, sx, d1[1], d2[1], d3[1], d4[1]);
                 beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
-                SELW(posv, wv, 0); diffs_mem(s_vt + offx, sx, d1[1], d2[1], d3[1], d4[1]);
+                UPD(posv, pv, ZP, 0); diffs_mem(s_vt + offx, sx, d1[1], d2[1], d3[1], d4[1]);
                 beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
-                SELW(posv, wz, 0); diffs_mem(s_z + offx, sx, d1[1], d2[1], d3[1], d4[1], cz1);
+                UPDC(posv, pz, ZP, 0, cz0); diffs_mem(s_z + offx, sx, d1[1], d2[1], d3[1], d4[1], cz1);
                 corr_n<2>(d1, d2, d3, d4, c0, c1, c2, num2, den);
                 rc[0] = den[0]; rc[1] = den[1];
             }
-            {   // flux quartet: h, A through the north face (windows), h, A through the west face (memory)
+            {   // flux quartet: h, A through the north face, h, A through the west face
                 double d1[4], d2[4], d3[4], d4[4], c0[4] = {es1, es1, es1, es1}, c1[4] = {es1, es1, es1, es1}, c2[4] = {es1, es1, es1, es1}, den[4];
-                SELW(posN, wh, 0); SELW(posN, wA, 1);
+                UPDC(posN, ph, W, 0, ch0); UPDC(posN, pA, W, 1, cA1);
                 diffs_mem(qh, sp, d1[2], d2[2], d3[2], d4[2], ch2);
                 diffs_mem(qA, sp, d1[3], d2[3], d3[3], d4[3], cA3);
                 beta_acc_n<4>(d1, d2, d3, d4, c0, c1, c2);
                 corr_n<4>(d1, d2, d3, d4, c0, c1, c2, num4, den);
                 rc[2] = den[0]; rc[3] = den[1]; rc[4] = den[2]; rc[5] = den[3];
             }
-            const double hc = wh.q2, hw_ = RAW(s_h, li - 1, lj), hs = RAW(s_h, li, lj - 1);
+            const double hc = ph[-W], hw_ = RAW(s_h, li - 1, lj), hs = RAW(s_h, li, lj - 1);
             rc[6] = 0.5 * (hw_ + hc);                                   // ℑx h
             rc[7] = 0.5 * (hs + hc);                                    // ℑy h
             {
@@ -281,15 +251,15 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
                 for (int n = 0; n < 8; n++) x[n] = rc[n];
                 rcp_n<8>(x, rc);
             }
-            const double zy = fma(posv ? num2[0] : -num2[0], rc[0], posv ? wz.q2 : wz.q3);
+            const double zy = fma(num2[0], rc[0], cz0);
             const double zx = fma(num2[1], rc[1], cz1);
-            const double wh_ = vN * fma(posN ? num4[0] : -num4[0], rc[2], posN ? wh.q2 : wh.q3);
-            const double wA_ = vN * fma(posN ? num4[1] : -num4[1], rc[3], posN ? wA.q2 : wA.q3);
+            const double wh_ = vN * fma(num4[0], rc[2], ch0);
+            const double wA_ = vN * fma(num4[1], rc[3], cA1);
             const double fxh = uw * fma(num4[2], rc[4], ch2);
             const double fxA = uw * fma(num4[3], rc[5], cA3);
-            fyh_n = bufN ? vN * sym2(wh.q2, wh.q3) : wh_;
-            fyA_n = bufN ? vN * sym2(wA.q2, wA.q3) : wA_;
-            const double adv_u = vhat * (ybuf(p.by, gj + 1, 3, p.NyG + 1) ? sym2(wz.q2, wz.q3) : zy);
+            fyh_n = bufN ? vN * sym2(hc, ph[0]) : wh_;
+            fyA_n = bufN ? vN * sym2(pA[-W], pA[0]) : wA_;
+            const double adv_u = vhat * (ybuf(p.by, gj + 1, 3, p.NyG + 1) ? sym2(pz[-ZP], pz[0]) : zy);
             const double adv_v = uhat * zx;
             // east faces: the neighbour lane's west face; lane 31 takes the pre-pass value
             double fxh_e = __shfl_down_sync(0xffffffffu, fxh, 1), fxA_e = __shfl_down_sync(0xffffffffu, fxA, 1);
@@ -297,7 +267,7 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
             if (lane == 31) { fxh_e = eh; fxA_e = eA; }
 
             double Gn0, Gn1, Gn2, Gn3;
-            const double Ac = wA.q2, An = wA.q3, As = RAW(s_A, li, lj - 1);
+            const double Ac = pA[-W], An = pA[0], As = RAW(s_A, li, lj - 1);
             const double Aw = RAW(s_A, li - 1, lj), Awn = RAW(s_A, li - 1, lj + 1), Aws = RAW(s_A, li - 1, lj - 1);
             {   // Gu at fcc — lorentz_force_func_x, sw_mhd_jacobian_functions.jl:10-13,20-22 — and
                 // Gv at cfc — lorentz_force_func_y, :15-18,24-26 — advanced together
@@ -344,11 +314,6 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
         }
         // slide to the next row
         fyh_s = fyh_n; fyA_s = fyA_n; vC = vN; vW = vWn;
-        if (it + 1 < R) {
-            const int bn = lj + 4;
-            win_push(wz, Zf(s_z, li, bn)); win_push(wu, Zf(s_ut, li, bn)); win_push(wv, Zf(s_vt, li, bn));
-            win_push(wh, RAW(s_h, li, bn)); win_push(wA, RAW(s_A, li, bn));
-        }
     }
 
     // ---- fused diagnostics of the state at the start of the step --------------------------
