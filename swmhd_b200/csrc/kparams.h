@@ -66,9 +66,11 @@ constexpr int NDIAG = 9; // sums: ke, me, pe, sum_h [0..3]; maxima: |u|, |A|, -h
 cudaError_t launch_substage_strict(const KParams &p, int form, int stage, cudaStream_t st);
 cudaError_t launch_substage_fast(const KParams &p, int form, int stage, cudaStream_t st);
 void substage_tile(int *tx, int *ty);
-// row-blocked variant (Jacobian form, FAST arithmetic, TMA): stages 1..3
-cudaError_t launch_substage_rb(const KParams &p, int stage, cudaStream_t st);
+// row-blocked kernels (substage_rb.cu; FAST arithmetic, TMA): stages 1..3 of either formulation
+cudaError_t launch_substage_rb(const KParams &p, int form, int stage, cudaStream_t st);
 void substage_rb_tile(int *tx, int *ty);
+int substage_rb_tiles_x(int form, int Nx);    // tiles per tile row (the divergence kernel owns 31 cells per tile row)
+int substage_rb_stage_mask();                 // SWMHD_RB_STAGES: bit s-1 = stage s runs the row-blocked kernel (default 7)
 cudaError_t launch_halo(const HaloParams &p, cudaStream_t st);
 cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st);
 cudaError_t launch_diag_final(const double *partials, int nblocks, double *stage, double *out9, cudaStream_t st);

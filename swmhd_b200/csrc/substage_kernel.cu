@@ -895,13 +895,10 @@ cudaError_t LAUNCH_NAME(const KParams &p, int form, int stage, cudaStream_t st) 
     const bool dg = (p.diag != nullptr);
     if (dg && stage != 1) return cudaErrorInvalidValue;
 #if !SWMHD_STRICT
-    // Jacobian form with TMA: the row-blocked kernel (substage_rb.cu); SWMHD_RB_STAGES masks stages
+    // FAST arithmetic with TMA: the row-blocked kernels (substage_rb.cu); SWMHD_RB_STAGES masks stages
     // (bit s-1 = stage s, default 7 = all) for A/B runs against this file's kernel.
-    if (form == 0 && stage >= 1 && p.use_tma && p.use_rb) {
-        static int mask = -1;
-        if (mask < 0) { const char *e = getenv("SWMHD_RB_STAGES"); mask = e ? atoi(e) : 7; }
-        if ((mask >> (stage - 1)) & 1) return launch_substage_rb(p, stage, st);
-    }
+    if (stage >= 1 && p.use_tma && p.use_rb && ((substage_rb_stage_mask() >> (stage - 1)) & 1))
+        return launch_substage_rb(p, form, stage, st);
 #endif
     switch (form * 4 + stage) {
         case 0: return launch_one<0, 0, false>(p, st);
@@ -918,6 +915,12 @@ cudaError_t LAUNCH_NAME(const KParams &p, int form, int stage, cudaStream_t st) 
 
 #if SWMHD_STRICT
 void substage_tile(int *tx, int *ty) { *tx = TX; *ty = TY; }
+#else
+int substage_rb_stage_mask() {
+    static int mask = -1;
+    if (mask < 0) { const char *e = getenv("SWMHD_RB_STAGES"); mask = e ? atoi(e) : 7; }
+    return mask;
+}
 #endif
 
 } // namespace swmhd

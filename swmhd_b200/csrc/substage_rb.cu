@@ -424,42 +424,395 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     }
 }
 
+// =====================================================================================================
+// Divergence (conservative) formulation, FAST arithmetic: ConservativeFormulation tendencies
+// with div_lorentz_x/y of divergence_formulation/sw_mhd_divergence_functions.jl:1-170 inlined.
+//
+// Same warp-private row walk.  Per row a thread evaluates the three x-type fluxes anchored at its column
+// (F_uu - Lxx at the ccc point li-1, F_uv - Lxy at the ffc point li, the tracer transport flux at fcc li)
+// and the three y-type fluxes of the row's NORTH side (F_vu - Lyx at ffc (li, lj+1), F_vv - Lyy at ccc
+// (li, lj), the tracer flux at cfc (li, lj+1)), which stay in registers as the next row's south side.
+// The east neighbours of the x-type fluxes come from lane+1 by shuffle; lane 31 only supplies them:
+// a tile is 31 cells wide (32 faces), which costs 3 % of the lanes instead of a pre-pass over three
+// flux families.
+constexpr int TXD = TX - 1;                                // cells per tile row in the divergence kernel
+constexpr int BP = TX + 4, BR = TYB + 4;                   // hBx, hBy, Bx, By, 1/ℑx h, 1/ℑy h: a in [1,TX+4], b in [1,TYB+4]
+constexpr int HP = TX + 1, HR = TYB + 1;                   // 1/ℑxy h at ffc: a in [3,TX+3], b in [3,TYB+3]
+constexpr int RP = TX + 2, RR = TYB + 2;                   // 1/h at ccc: a in [2,TX+3], b in [2,TYB+3]
+constexpr int NB = BP * BR, NH = HP * HR, NRH = RP * RR;
+constexpr int DERIVED_D = 6 * NB + NH + NRH;
+constexpr size_t SMEM_BYTES_D = ((size_t)4 * SZP + DERIVED_D + 2 + NW * NDIAG) * sizeof(double);
+#define Bf(arr, a, b) arr[((b) - 1) * BP + (a) - 1]
+#define RHF(a, b) s_rhff[((b) - 3) * HP + (a) - 3]
+#define RH(a, b) s_rh[((b) - 2) * RP + (a) - 2]
+
+__device__ __forceinline__ double sym4(double a, double b, double c, double d) {
+    return fma(7.0 / 12.0, b + c, (-1.0 / 12.0) * (a + d));
+}
+// third-order biased interpolants of sw_mhd_divergence_functions.jl:25-35
+__device__ __forceinline__ double third(double x2, double x5, double xm) {      // (2*x2 + 5*x5 - xm)/6
+    return fma(1.0 / 3.0, x2, fma(5.0 / 6.0, x5, (-1.0 / 6.0) * xm));
+}
+__device__ __forceinline__ double thirdR(double xm, double x5, double x2) {     // (-xm + 5*x5 + 2*x2)/6
+    return fma(-1.0 / 6.0, xm, fma(5.0 / 6.0, x5, (1.0 / 3.0) * x2));
+}
+__device__ __forceinline__ double upwind_sel(double vel, double L, double Rr) { return vel * (vel > 0.0 ? L : Rr); }
+
 template <int STAGE, bool DIAG>
+__global__ void __launch_bounds__(NT, RB_MINB) substage_rbd_kernel(const __grid_constant__ KParams p) {
+    extern __shared__ __align__(128) unsigned char smem_bytes[];
+    double *const s_u = reinterpret_cast<double *>(smem_bytes);
+    double *const s_v = s_u + SZP, *const s_h = s_u + 2 * SZP, *const s_A = s_u + 3 * SZP;
+    double *const smem = s_u + 4 * SZP;
+    double *const s_hBx = smem, *const s_hBy = smem + NB, *const s_Bx = smem + 2 * NB, *const s_By = smem + 3 * NB;
+    double *const s_rhx = smem + 4 * NB, *const s_rhy = smem + 5 * NB;      // 1/ℑx h, 1/ℑy h
+    double *const s_rhff = smem + 6 * NB, *const s_rh = s_rhff + NH;        // 1/ℑxy h at ffc, 1/h at ccc
+    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + DERIVED_D);
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int Nx = p.Nx, P = p.P;
+    const double eps = p.eps;
+    const int tiles_x = (Nx + TXD - 1) / TXD;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int row0 = p.row_begin + tile_y * TYB;            // 0-based first cell row = parent row of b = 0
+
+    // ---- P0: stage uh,vh,h,A with a 3-cell halo (same boxes as the Jacobian kernel) ------------------
+    if (tid == 0) {
+        mbar_init(mbar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(mbar, TILE_TX_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; k++) tma_load_2d(s_u + k * SZP, &p.tm_rb[k], (tile_x * TXD) & ~1, row0, mbar);
+#if RB_L2_PREFETCH
+        const int nxt = blockIdx.x + p.l2_ahead;             // the tile of the CTA that takes over this slot, into L2
+        if (nxt < gridDim.x) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) tma_prefetch_2d(&p.tm_rb[k], ((nxt % tiles_x) * TXD) & ~1, p.row_begin + (nxt / tiles_x) * TYB);
+        }
+#endif
+    }
+    // the box starts at an even parent column (16-byte aligned source address; an odd start raised an
+    // illegal-instruction fault): tiles with an odd first column sit one column further right in the box
+    const int li = lane + 3 + ((tile_x * TXD) & 1), lj0 = 3 + wp * R;   // tile-local column / first row of this thread
+    const int i = tile_x * TXD + 1 + lane;                  // logical (1-based) column
+    const bool own = (lane < TXD) && (i <= Nx);             // lane 31 only supplies east-neighbour fluxes
+    const int jc0 = row0 + 1 + wp * R;                      // logical (1-based, slab-local) first row
+    const int gj0 = p.gj0 + jc0;                            // global row of the first cell (wall logic)
+    const int NyG = p.NyG, by = p.by;
+    double Gq0 = 0.0, Gq1 = 0.0, Gq2 = 0.0, Gq3 = 0.0;      // G^- of the row in flight
+    if constexpr (STAGE >= 2) {
+        if (own && (jc0 <= p.row_end)) {
+            const size_t g0 = (size_t)(i + 2) + (size_t)P * (size_t)(jc0 + 2);
+            Gq0 = p.G[0][g0]; Gq1 = p.G[1][g0]; Gq2 = p.G[2][g0]; Gq3 = p.G[3][g0];
+        }
+    }
+    __syncthreads();                                        // barrier initialised before anybody polls it
+    mbar_wait(mbar, 0);
+
+    // ---- A: hBx, hBy, Bx, By (sw_mhd_divergence_functions.jl:134-148) and the reciprocal depths ---------
+#pragma unroll 2
+    for (int t = tid; t < NB; t += NT) {
+        const int a = 1 + t % BP, b = 1 + t / BP;
+        // telescoped ℑxy∂: hBx = -(ℑxy ∂y A), hBy = ℑxy ∂x A
+        const double hbx = ((RAW(s_A, a - 1, b - 1) + RAW(s_A, a, b - 1)) - (RAW(s_A, a - 1, b + 1) + RAW(s_A, a, b + 1))) * (0.25 * p.rdy);
+        const double hby = ((RAW(s_A, a + 1, b - 1) + RAW(s_A, a + 1, b)) - (RAW(s_A, a - 1, b - 1) + RAW(s_A, a - 1, b))) * (0.25 * p.rdx);
+        const double hc = RAW(s_h, a, b);
+        const double rhx = frcp(0.5 * (RAW(s_h, a - 1, b) + hc)), rhy = frcp(0.5 * (RAW(s_h, a, b - 1) + hc));
+        s_hBx[t] = hbx; s_hBy[t] = hby;
+        s_rhx[t] = rhx; s_rhy[t] = rhy;
+        s_Bx[t] = hbx * rhx; s_By[t] = hby * rhy;
+    }
+    for (int t = tid; t < NH + NRH; t += NT) {
+        if (t < NH) {
+            const int a = 3 + t % HP, b = 3 + t / HP;
+            s_rhff[t] = frcp(avg4(RAW(s_h, a - 1, b - 1), RAW(s_h, a, b - 1), RAW(s_h, a - 1, b), RAW(s_h, a, b)));
+        } else {
+            const int q = t - NH, a = 2 + q % RP, b = 2 + q / RP;
+            s_rh[q] = frcp(RAW(s_h, a, b));
+        }
+    }
+    __syncthreads();
+
+    // ---- B/C: warp-private row walk ----------------------------------------------------------------------
+    const double es = eps * (12.0 / 13.0);
+    double Fvu_s = 0.0, Fvv_s = 0.0, Ty_s = 0.0, vq_s = 0.0;   // south side of the current row (from the previous iteration)
+    double dg[NDIAG];
+    if constexpr (DIAG) {
+#pragma unroll
+        for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
+        dg[6] = -INFINITY;
+    }
+    (void)dg;
+
+#pragma unroll 1
+    for (int it = -1; it < R; ++it) {
+        const int lj = lj0 + it, ln = lj + 1;               // current row, north face row
+        const int j = jc0 + it, gj = gj0 + it;
+        const bool active = own && (j <= p.row_end);
+        const size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(j + 2);
+        const double Gm0 = Gq0, Gm1 = Gq1, Gm2 = Gq2, Gm3 = Gq3;
+        if constexpr (STAGE >= 2) {
+            if (it >= 0 && it + 1 < R && own && (j + 1 <= p.row_end)) {
+                const size_t gn = gcell + (size_t)P;
+                Gq0 = p.G[0][gn]; Gq1 = p.G[1][gn]; Gq2 = p.G[2][gn]; Gq3 = p.G[3][gn];
+            }
+        }
+        // ---- north side: F_vu - Lyx at ffc (li, ln), F_vv - Lyy at ccc (li, lj), tracer flux at cfc (li, ln) ----
+        double Fvu_n, Fvv_c, Ty_n, vq_n;
+        {
+            const double vln = RAW(s_v, li, ln);
+            double vel[3];
+            vel[0] = sym4(RAW(s_v, li - 2, ln), RAW(s_v, li - 1, ln), vln, RAW(s_v, li + 1, ln));
+            {
+                const double vc = RAW(s_v, li, lj);
+                const double v2 = sym2(vc, vln), v4 = sym4(RAW(s_v, li, lj - 1), vc, vln, RAW(s_v, li, lj + 2));
+                vel[1] = ybuf(by, gj + 1, 2, NyG + 1) ? v2 : v4;
+            }
+            vel[2] = vln;
+            const double *const cu = &RAW(s_u, li, ln), *const cv = &RAW(s_v, li, ln), *const cA = &RAW(s_A, li, ln);
+            double d1[3], d2[3], d3[3], d4[3], c0[3] = {es, es, es}, c1[3] = {es, es, es}, c2[3] = {es, es, es}, num[3], den[3], rc[3], cc[3];
+            UPDC(vel[0] > 0.0, cu, W, 0, cc[0]); UPDC(vel[1] > 0.0, cv, W, 1, cc[1]); UPDC(vel[2] > 0.0, cA, W, 2, cc[2]);
+            beta_acc_n<3>(d1, d2, d3, d4, c0, c1, c2);
+            corr_n<3>(d1, d2, d3, d4, c0, c1, c2, num, den);
+            rcp_n<3>(den, rc);
+            double fl[3];
+#pragma unroll
+            for (int n = 0; n < 3; n++) fl[n] = vel[n] * fma(num[n], rc[n], cc[n]);
+            // Bounded-y wall buffers: centred second order (oracle ybuf)
+            if (ybuf(by, gj + 1, 3, NyG)) { fl[0] = vel[0] * sym2(cu[-W], cu[0]); fl[2] = vel[2] * sym2(cA[-W], cA[0]); }
+            if (ybuf(by, gj + 1, 3, NyG + 1)) fl[1] = vel[1] * sym2(cv[-W], cv[0]);
+            {   // F_vu - Lyx (advective_lorentz_flux_hBy_bx, :62-84 with its edge branches)
+                const double mom = (p.dx * fl[0]) * RHF(li, ln);
+                const double vl = 0.5 * (Bf(s_hBy, li - 1, ln) + Bf(s_hBy, li, ln));
+                const double B0 = Bf(s_Bx, li, ln), Bm = Bf(s_Bx, li, ln - 1);
+                const double L3 = third(B0, Bm, Bf(s_Bx, li, ln - 2)), R3 = thirdR(Bf(s_Bx, li, ln + 1), B0, Bm);
+                double Lq = L3, Rq = R3;
+                if (by) {
+                    const int gjf = gj + 1;
+                    if (gjf == 1) { Lq = B0; Rq = B0; } else if (gjf == 2) { Lq = Bm; Rq = R3; }
+                    else if (gjf == NyG) { Lq = L3; Rq = B0; } else if (gjf == NyG + 1) { Lq = Bm; Rq = Bm; }
+                }
+                Fvu_n = p.dx * upwind_sel(vl, Lq, Rq) - mom;
+            }
+            {   // F_vv - Lyy (advective_lorentz_flux_hBy_by, :110-132)
+                const double mom = (p.dx * fl[1]) * RH(li, lj);
+                const double vl = 0.5 * (Bf(s_hBy, li, lj) + Bf(s_hBy, li, ln));
+                const double B0 = Bf(s_By, li, lj), Bp = Bf(s_By, li, ln);
+                const double L3 = third(Bp, B0, Bf(s_By, li, lj - 1)), R3 = thirdR(Bf(s_By, li, lj + 2), Bp, B0);
+                double Lq = L3, Rq = R3;
+                if (by) {
+                    if (gj == 0) { Lq = Bp; Rq = Bp; } else if (gj == 1) { Lq = B0; Rq = R3; }
+                    else if (gj == NyG - 1) { Lq = L3; Rq = Bp; } else if (gj == NyG) { Lq = B0; Rq = B0; }
+                }
+                Fvv_c = p.dx * upwind_sel(vl, Lq, Rq) - mom;
+            }
+            {   // tracer transport flux and vh/ℑy h at cfc (li, ln)
+                const double rhy = Bf(s_rhy, li, ln);
+                Ty_n = (p.dx * fl[2]) * rhy;
+                vq_n = vln * rhy;
+            }
+        }
+        if (it >= 0) {
+            // ---- x side: F_uu - Lxx at ccc li-1, F_uv - Lxy at ffc li, tracer flux at fcc li ---------------------
+            const double uc = RAW(s_u, li, lj), ue = RAW(s_u, li + 1, lj), us = RAW(s_u, li, lj - 1);
+            double Fuu_w, Fuv_w, Tx_w, uq_w;
+            {
+                double vel[3];
+                vel[0] = sym4(RAW(s_u, li - 2, lj), RAW(s_u, li - 1, lj), uc, ue);
+                {
+                    const double u2 = sym2(us, uc), u4 = sym4(RAW(s_u, li, lj - 2), us, uc, RAW(s_u, li, lj + 1));
+                    vel[1] = ybuf(by, gj, 2, NyG) ? u2 : u4;
+                }
+                vel[2] = uc;
+                const double *const cu = &RAW(s_u, li, lj), *const cv = &RAW(s_v, li, lj), *const cA = &RAW(s_A, li, lj);
+                double d1[3], d2[3], d3[3], d4[3], c0[3] = {es, es, es}, c1[3] = {es, es, es}, c2[3] = {es, es, es}, num[3], den[3], rc[3], cc[3];
+                UPDC(vel[0] > 0.0, cu, 1, 0, cc[0]); UPDC(vel[1] > 0.0, cv, 1, 1, cc[1]); UPDC(vel[2] > 0.0, cA, 1, 2, cc[2]);
+                beta_acc_n<3>(d1, d2, d3, d4, c0, c1, c2);
+                corr_n<3>(d1, d2, d3, d4, c0, c1, c2, num, den);
+                rcp_n<3>(den, rc);
+                double fl[3];
+#pragma unroll
+                for (int n = 0; n < 3; n++) fl[n] = vel[n] * fma(num[n], rc[n], cc[n]);
+                {   // F_uu - Lxx (advective_lorentz_flux_hBx_bx, :38-60) at the ccc point li-1
+                    const double mom = (p.dy * fl[0]) * RH(li - 1, lj);
+                    const double ul = 0.5 * (Bf(s_hBx, li - 1, lj) + Bf(s_hBx, li, lj));
+                    const double B0 = Bf(s_Bx, li - 1, lj), Bp = Bf(s_Bx, li, lj);
+                    const double Lq = third(Bp, B0, Bf(s_Bx, li - 2, lj)), Rq = thirdR(Bf(s_Bx, li + 1, lj), Bp, B0);
+                    Fuu_w = p.dy * upwind_sel(ul, Lq, Rq) - mom;
+                }
+                {   // F_uv - Lxy (advective_lorentz_flux_hBx_by, :86-108) at the ffc point (li, lj)
+                    const double mom = (p.dy * fl[1]) * RHF(li, lj);
+                    const double ul = 0.5 * (Bf(s_hBx, li, lj - 1) + Bf(s_hBx, li, lj));
+                    const double B0 = Bf(s_By, li, lj), Bm = Bf(s_By, li - 1, lj);
+                    const double Lq = third(B0, Bm, Bf(s_By, li - 2, lj)), Rq = thirdR(Bf(s_By, li + 1, lj), B0, Bm);
+                    Fuv_w = p.dy * upwind_sel(ul, Lq, Rq) - mom;
+                }
+                {   // tracer transport flux and uh/ℑx h at fcc (li, lj)
+                    const double rhx = Bf(s_rhx, li, lj);
+                    Tx_w = (p.dy * fl[2]) * rhx;
+                    uq_w = uc * rhx;
+                }
+            }
+            const double Fuu_e = __shfl_down_sync(0xffffffffu, Fuu_w, 1), Fuv_e = __shfl_down_sync(0xffffffffu, Fuv_w, 1);
+            const double Tx_e = __shfl_down_sync(0xffffffffu, Tx_w, 1), uq_e = __shfl_down_sync(0xffffffffu, uq_w, 1);
+
+            // ---- tendencies ----------------------------------------------------------------------
+            // d(g h^2 / 2): h = 1 + O(1e-9) makes this a cancellation; keep the products un-contracted
+            const double hg = 0.5 * p.g;
+            const double hc = RAW(s_h, li, lj), hw_ = RAW(s_h, li - 1, lj), hs = RAW(s_h, li, lj - 1);
+            const double Pc = __dmul_rn(hg, __dmul_rn(hc, hc)), Pw = __dmul_rn(hg, __dmul_rn(hw_, hw_)), Ps = __dmul_rn(hg, __dmul_rn(hs, hs));
+            const double vc = RAW(s_v, li, lj), vn = RAW(s_v, li, ln);
+            double Gn0, Gn1 = 0.0, Gn2, Gn3;
+            {   // Guh (dm holds div(Lorentz - momentum flux))
+                const double dm = p.inv_az * ((Fuu_e - Fuu_w) + (Fvu_n - Fvu_s));
+                const double pg = __dsub_rn(Pc, Pw) * p.rdx;
+                const double vhat = avg4(RAW(s_v, li - 1, lj), vc, RAW(s_v, li - 1, ln), vn);
+                Gn0 = fma(p.f, vhat, dm - pg);
+            }
+            if (!(by && gj < 2)) {   // Gvh (wall rows of a Bounded-y grid keep vh = 0)
+                const double dm = p.inv_az * ((Fuv_e - Fuv_w) + (Fvv_c - Fvv_s));
+                const double pg = __dsub_rn(Pc, Ps) * p.rdy;
+                const double uhat = avg4(us, RAW(s_u, li + 1, lj - 1), uc, ue);
+                Gn1 = fma(-p.f, uhat, dm - pg);
+            }
+            {   // Gh (centred), GA
+                Gn2 = -fma(ue - uc, p.rdx, (vn - vc) * p.rdy);
+                const double d = p.inv_az * ((Tx_e - Tx_w) + (Ty_n - Ty_s));
+                const double cdiv = (uq_e - uq_w) * p.rdx + (vq_n - vq_s) * p.rdy;
+                Gn3 = -d + RAW(s_A, li, lj) * cdiv;
+            }
+            if (active) {
+                const double Gn[4] = {Gn0, Gn1, Gn2, Gn3};
+                const double Gm[4] = {Gm0, Gm1, Gm2, Gm3};
+                const double Uc[4] = {uc, vc, hc, RAW(s_A, li, lj)};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if constexpr (STAGE == 1) {
+                        p.Un[k][gcell] = Uc[k] + p.dtgam * Gn[k];
+                        p.G[k][gcell] = Gn[k];
+                    } else {
+                        p.Un[k][gcell] = Uc[k] + p.dt * (p.gam * Gn[k] + p.zet * Gm[k]);
+                        if constexpr (STAGE == 2) p.G[k][gcell] = Gn[k];
+                    }
+                }
+            }
+        }
+        Fvu_s = Fvu_n; Fvv_s = Fvv_c; Ty_s = Ty_n; vq_s = vq_n;
+    }
+
+    // ---- fused diagnostics of the state at the start of the step ------------------------------
+    if constexpr (DIAG) {
+        double *const s_red = smem + DERIVED_D + 2;
+        constexpr int NR = R + 2;                            // rows b = lj0-1 .. lj0+R, index k = b - (lj0-1)
+        auto sq = [](double x) { return x * x; };
+        double Ac[NR], Aw[NR], Ae[NR], sqy[NR], sqx[NR];
+#pragma unroll
+        for (int k = 0; k < NR; k++) {
+            const int b = lj0 - 1 + k;
+            Ac[k] = RAW(s_A, li, b); Aw[k] = RAW(s_A, li - 1, b); Ae[k] = RAW(s_A, li + 1, b);
+            sqy[k] = sq(((Ac[k] - Aw[k]) * p.rdx) * Bf(s_rhx, li, b));                       // (dxA / ℑx h)^2 at fcc
+        }
+        sqx[0] = 0.0;
+#pragma unroll
+        for (int k = 1; k < NR; k++) sqx[k] = sq(-((Ac[k] - Ac[k - 1]) * p.rdy) * Bf(s_rhy, li, lj0 - 1 + k));   // (dyA / ℑy h)^2 at cfc
+        double uu[R], vc[R + 1], kb[R];
+        {
+            double vw2[R + 1], vc2[R + 1];
+#pragma unroll
+            for (int k = 0; k <= R; k++) { vc[k] = RAW(s_v, li, lj0 + k); vc2[k] = sq(vc[k]); vw2[k] = sq(RAW(s_v, li - 1, lj0 + k)); }
+#pragma unroll
+            for (int r = 0; r < R; r++) {                    // KE bracket uh^2 + ℑxyᶠᶜᵃ(vh^2) at fcc(li)
+                uu[r] = RAW(s_u, li, lj0 + r);
+                kb[r] = sq(uu[r]) + avg4(vw2[r], vc2[r], vw2[r + 1], vc2[r + 1]);
+            }
+        }
+        double sqye[NR], kbe[R];                             // east neighbours (lane 31 holds the column beyond the tile)
+#pragma unroll
+        for (int k = 0; k < NR; k++) sqye[k] = __shfl_down_sync(0xffffffffu, sqy[k], 1);
+#pragma unroll
+        for (int r = 0; r < R; r++) kbe[r] = __shfl_down_sync(0xffffffffu, kb[r], 1);
+        double mb[R + 1];
+#pragma unroll
+        for (int k = 1; k < NR; k++) mb[k - 1] = sqx[k] + avg4(sqy[k - 1], sqye[k - 1], sqy[k], sqye[k]);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int j = jc0 + r, k = r + 1, lj = lj0 + r;
+            if (own && (j <= p.row_end)) {
+                const double hh = RAW(s_h, li, lj), aa = Ac[k], rh = RH(li, lj);
+                dg[0] += (0.5 * rh) * (0.5 * (kb[r] + kbe[r]));
+                dg[1] += (0.5 * hh) * (0.5 * (mb[r] + mb[r + 1]));
+                const double dh = hh - p.h_ref;
+                dg[2] += (0.5 * p.g) * (dh * dh);
+                dg[3] += hh;
+                dg[4] = fmax(dg[4], fabs(uu[r] * Bf(s_rhx, li, lj)));
+                dg[5] = fmax(dg[5], fabs(aa));
+                dg[6] = fmax(dg[6], -hh);
+                {
+                    const double hbx0 = (Aw[k - 1] + Ac[k - 1]) - (Aw[k + 1] + Ac[k + 1]), hbx1 = (Ac[k - 1] + Ae[k - 1]) - (Ac[k + 1] + Ae[k + 1]);
+                    const double hby0 = (Ae[k - 1] + Ae[k]) - (Aw[k - 1] + Aw[k]), hby1 = (Ae[k] + Ae[k + 1]) - (Aw[k] + Aw[k + 1]);
+                    dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
+                }
+                if (!(isfinite(hh) && isfinite(aa) && isfinite(uu[r]) && isfinite(vc[r]))) dg[8] += 1.0;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NDIAG; q++) {
+            const bool is_max = (q >= 4 && q <= 7);
+            const double x = is_max ? warp_max(dg[q]) : warp_sum(dg[q]);
+            if (lane == 0) s_red[wp * NDIAG + q] = x;
+        }
+        __syncthreads();
+        if (tid < NDIAG) {
+            const bool is_max = (tid >= 4 && tid <= 7);
+            double acc = s_red[tid];
+            for (int w2 = 1; w2 < NW; w2++) { const double x = s_red[w2 * NDIAG + tid]; acc = is_max ? fmax(acc, x) : acc + x; }
+            const int tr8 = row0 / 8;
+            p.diag[((size_t)tr8 * tiles_x + tile_x) * NDIAG + tid] = acc;
+            for (int s2 = 1; s2 < TYB / 8; s2++)
+                if (row0 + 8 * s2 < p.row_end) p.diag[((size_t)(tr8 + s2) * tiles_x + tile_x) * NDIAG + tid] = (tid == 6) ? -INFINITY : 0.0;
+        }
+    }
+}
+
+template <int FORM, int STAGE, bool DIAG>
 cudaError_t launch_rb(const KParams &p, cudaStream_t st) {
-    auto kern = substage_rb_kernel<STAGE, DIAG>;
+    auto kern = (FORM == 0) ? substage_rb_kernel<STAGE, DIAG> : substage_rbd_kernel<STAGE, DIAG>;
+    constexpr size_t bytes = (FORM == 0) ? SMEM_BYTES : SMEM_BYTES_D;
+    constexpr int cells_x = (FORM == 0) ? TX : TXD;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const int tiles_x = (p.Nx + TX - 1) / TX;
+    const int tiles_x = (p.Nx + cells_x - 1) / cells_x;
     const int tiles_y = (p.row_end - p.row_begin + TYB - 1) / TYB;
     static int ahead = -1;
     if (ahead < 0) {
         int dev = 0, sms = 0, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, SMEM_BYTES);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, bytes);
         if (e != cudaSuccess) return e;
         const char *env = getenv("SWMHD_L2_AHEAD");
         ahead = env ? atoi(env) : (occ < 1 ? 1 : occ) * sms;   // CTAs in flight = distance to the slot's next tile
     }
     KParams q = p;
     q.l2_ahead = ahead;
-    kern<<<tiles_x * tiles_y, NT, SMEM_BYTES, st>>>(q);
+    kern<<<tiles_x * tiles_y, NT, bytes, st>>>(q);
     return cudaGetLastError();
 }
 
 } // namespace
 
 void substage_rb_tile(int *tx, int *ty) { *tx = TX; *ty = TYB; }
+int substage_rb_tiles_x(int form, int Nx) { const int c = (form == 0) ? TX : TXD; return (Nx + c - 1) / c; }
 
-cudaError_t launch_substage_rb(const KParams &p0, int stage, cudaStream_t st) {
+cudaError_t launch_substage_rb(const KParams &p0, int form, int stage, cudaStream_t st) {
     if (p0.tile_rows <= 0) return cudaSuccess;
     if (!p0.use_rb) return cudaErrorInvalidValue;
     int tx8, ty8;
     substage_tile(&tx8, &ty8);                              // launch granularity of the host side (tile rows)
+    if (ty8 != 8) return cudaErrorInvalidValue;
     KParams p = p0;
     p.row_begin = p0.tile_row0 * ty8;
     p.row_end = (p0.tile_row0 + p0.tile_rows) * ty8;
@@ -467,10 +820,13 @@ cudaError_t launch_substage_rb(const KParams &p0, int stage, cudaStream_t st) {
     if (p.row_end <= p.row_begin) return cudaSuccess;
     const bool dg = (p.diag != nullptr);
     if (dg && stage != 1) return cudaErrorInvalidValue;
-    switch (stage) {
-        case 1: return dg ? launch_rb<1, true>(p, st) : launch_rb<1, false>(p, st);
-        case 2: return launch_rb<2, false>(p, st);
-        case 3: return launch_rb<3, false>(p, st);
+    switch (form * 4 + stage) {
+        case 1: return dg ? launch_rb<0, 1, true>(p, st) : launch_rb<0, 1, false>(p, st);
+        case 2: return launch_rb<0, 2, false>(p, st);
+        case 3: return launch_rb<0, 3, false>(p, st);
+        case 5: return dg ? launch_rb<1, 1, true>(p, st) : launch_rb<1, 1, false>(p, st);
+        case 6: return launch_rb<1, 2, false>(p, st);
+        case 7: return launch_rb<1, 3, false>(p, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -154,8 +154,8 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
         for (int k = 0; k < 4 && ctx->use_tma; k++)
             if (!encode_field_map(&ctx->tmap[b][k], ctx->U[b][k], ctx->P, ctx->rows[k], ctx->tx + 6, ctx->ty + 6)) ctx->use_tma = 0;
     if (getenv("SWMHD_NO_TMA")) ctx->use_tma = 0;
-    // row-blocked kernel (Jacobian form, FAST): taller box; its 8-row launch granularity is ctx->ty
-    ctx->use_rb = (ctx->use_tma && ctx->ty == 8 && c->formulation == SWMHD_JACOBIAN && c->arith == SWMHD_ARITH_FAST) ? 1 : 0;
+    // row-blocked kernels (FAST arithmetic): taller box; their 8-row launch granularity is ctx->ty
+    ctx->use_rb = (ctx->use_tma && ctx->ty == 8 && c->arith == SWMHD_ARITH_FAST) ? 1 : 0;
     if (ctx->use_rb) {
         int rtx, rty;
         substage_rb_tile(&rtx, &rty);
@@ -164,8 +164,11 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
                 if (!encode_field_map(&ctx->tmap_rb[b][k], ctx->U[b][k], ctx->P, ctx->rows[k], rtx + 6, rty + 6)) ctx->use_rb = 0;
     }
     if (getenv("SWMHD_NO_RB")) ctx->use_rb = 0;
+    // per-tile diagnostic partials: one slot per (8-row tile row, tile column) of the kernel that runs stage 1
+    const int diag_tiles_x = (ctx->use_rb && (substage_rb_stage_mask() & 1)) ? substage_rb_tiles_x(c->formulation, ctx->Nx)
+                                                                             : (ctx->Nx + ctx->tx - 1) / ctx->tx;
     ctx->nblocks_diag = diag_blocks(ctx->Nx, ctx->Ny);
-    ctx->ntiles = ((ctx->Nx + ctx->tx - 1) / ctx->tx) * ctx->ntr;
+    ctx->ntiles = diag_tiles_x * ctx->ntr;
     if (ctx->ntiles > ctx->nblocks_diag) ctx->nblocks_diag = ctx->ntiles;   // d_partials serves both diag paths
     ctx->diag_slots = 1024;
     if ((e = cudaMalloc(&ctx->d_partials, (size_t)ctx->nblocks_diag * NDIAG * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
