@@ -13,8 +13,8 @@
 //     instead of three, and no flux arrays in shared memory.
 //   * the next tile of the SM slot is pulled into L2 while this one computes (cp.async.bulk.prefetch).
 //
-// Measured (profiles/README.md): 0.714 / 0.752 / 0.726 ms per stage at 4096^2 against 0.756 / 0.782 /
-// 0.743 ms of the one-thread-per-cell kernel; with the fused diagnostics 0.87 vs 1.06 ms.  A variant
+// Measured (profiles/README.md): 0.67 / 0.72 / 0.70 ms per stage at 4096^2 against 0.756 / 0.782 /
+// 0.743 ms of the one-thread-per-cell kernel; with the fused diagnostics 0.84 vs 1.06 ms.  A variant
 // that also kept the y stencils in sliding register windows was slower (register moves and selects
 // outweighed the saved shared-memory loads): see the history table there.
 // Arithmetic per value is the FAST arithmetic of substage_kernel.cu (same operation order).
@@ -32,8 +32,11 @@ namespace {
 #ifndef RB_R
 #define RB_R 4
 #endif
-#ifndef RB_MINB
-#define RB_MINB 3
+#ifndef RB_MINB            // CTAs per SM the Jacobian kernel is compiled for (<= 128 registers, 55.6 KB of shared memory)
+#define RB_MINB 4
+#endif
+#ifndef RB_MINB_D          // the divergence kernel: 71 KB of shared memory
+#define RB_MINB_D 3
 #endif
 #ifndef RB_L2_PREFETCH
 #define RB_L2_PREFETCH 1
@@ -47,7 +50,7 @@ constexpr unsigned TILE_TX_BYTES = 4u * SZ * 8u;
 constexpr int ZP = TX + 5, ZR = TYB + 5;                   // ffc points a in [1,TX+5], b in [1,TYB+5]
 constexpr int CP = TX + 2, CR = TYB + 2;                   // ccc points a in [2,TX+3], b in [2,TYB+3]
 constexpr int NZ = ZP * ZR, NC = CP * CR;
-constexpr int o_z = 0, o_ut = NZ, o_vt = 2 * NZ, o_K = 3 * NZ, o_Bx = o_K + NC, o_By = o_Bx + NC;
+constexpr int o_z = 0, o_ut = NZ, o_vt = 2 * NZ, o_Bx = 3 * NZ, o_By = o_Bx + NC;
 constexpr int DERIVED = o_By + NC;
 constexpr size_t SMEM_BYTES = ((size_t)4 * SZP + DERIVED + 2 + NW * NDIAG) * sizeof(double);   // + mbarrier + DIAG partials
 
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     double *const s_v = s_u + SZP, *const s_h = s_u + 2 * SZP, *const s_A = s_u + 3 * SZP;
     double *const smem = s_u + 4 * SZP;
     double *const s_z = smem + o_z, *const s_ut = smem + o_ut, *const s_vt = smem + o_vt;
-    double *const s_K = smem + o_K, *const s_Bx = smem + o_Bx, *const s_By = smem + o_By;
+    double *const s_Bx = smem + o_Bx, *const s_By = smem + o_By;
     uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + DERIVED);
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int Nx = p.Nx, P = p.P;
@@ -147,10 +150,8 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
         s_vt[q] = 0.5 * (vw + vc);
     }
 #pragma unroll 3
-    for (int q = tid; q < NC; q += NT) {                    // K, Bx, By at ccc (sw_mhd_jacobian_functions.jl:1-7)
+    for (int q = tid; q < NC; q += NT) {                    // Bx, By at ccc (sw_mhd_jacobian_functions.jl:1-7)
         const int a = 2 + q % CP, b = 2 + q / CP;
-        const double u0 = RAW(s_u, a, b), u1 = RAW(s_u, a + 1, b), v0 = RAW(s_v, a, b), v1 = RAW(s_v, a, b + 1);
-        s_K[q] = 0.25 * (fma(u0, u0, u1 * u1) + fma(v0, v0, v1 * v1));
         const double rh = frcp(RAW(s_h, a, b));
         s_Bx[q] = ((RAW(s_A, a, b - 1) - RAW(s_A, a, b + 1)) * (0.5 * p.rdy)) * rh;
         s_By[q] = ((RAW(s_A, a + 1, b) - RAW(s_A, a - 1, b)) * (0.5 * p.rdx)) * rh;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     // Row loop.  Iteration it = -1 only produces the fluxes through the south face of the warp's first
     // row; every other iteration evaluates the NORTH face lj+1 of its row and keeps it for the next one.
     double vC = RAW(s_v, li, lj0 - 1), vW = RAW(s_v, li - 1, lj0 - 1);
-    double fyh_s = 0.0, fyA_s = 0.0;
+    double fyh_s = 0.0, fyA_s = 0.0, K_s = 0.0;
     double dg[NDIAG];
     if constexpr (DIAG) {
 #pragma unroll
@@ -198,6 +199,10 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
         const double es1 = eps * (12.0 / 13.0), es2 = eps * (24.0 / 13.0);
         double fyh_n, fyA_n;
         const double *const ph = &RAW(s_h, li, lj + 1), *const pA = &RAW(s_A, li, lj + 1);   // north face lj+1
+        // kinetic energy K at ccc (li, lj), in registers: the row walk keeps it as the next row's K(li, lj-1)
+        // (a phase-A array of K would push the tile over the shared memory of 4 CTAs per SM)
+        const double uwk = RAW(s_u, li, lj), uek = RAW(s_u, li + 1, lj);
+        const double Kc = 0.25 * (fma(uwk, uwk, uek * uek) + fma(vC, vC, vN * vN));
         if (it < 0) {
             // south face of the warp's first row: h and A fluxes
             double d1[2], d2[2], d3[2], d4[2], c0[2] = {es1, es1}, c1[2] = {es1, es1}, c2[2] = {es1, es1}, num[2], den[2], rc[2];
@@ -271,9 +276,10 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
             const double Aw = RAW(s_A, li - 1, lj), Awn = RAW(s_A, li - 1, lj + 1), Aws = RAW(s_A, li - 1, lj - 1);
             {   // Gu at fcc — lorentz_force_func_x, sw_mhd_jacobian_functions.jl:10-13,20-22 — and
                 // Gv at cfc — lorentz_force_func_y, :15-18,24-26 — advanced together
-                const double Kc = Cc(s_K, li, lj);
-                const double dKx = (Kc - Cc(s_K, li - 1, lj)) * p.rdx;
-                const double dKy = (Kc - Cc(s_K, li, lj - 1)) * p.rdy;
+                const double uww = RAW(s_u, li - 1, lj);
+                const double Kw = 0.25 * (fma(uww, uww, uw * uw) + fma(vW, vW, vWn * vWn)); // K at ccc (li-1, lj)
+                const double dKx = (Kc - Kw) * p.rdx;
+                const double dKy = (Kc - K_s) * p.rdy;
                 const double pgx = p.g * ((hc - hw_) * p.rdx);
                 const double pgy = p.g * ((hc - hs) * p.rdy);
                 const double dxA = (Ac - Aw) * p.rdx;
@@ -313,7 +319,7 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
             }
         }
         // slide to the next row
-        fyh_s = fyh_n; fyA_s = fyA_n; vC = vN; vW = vWn;
+        fyh_s = fyh_n; fyA_s = fyA_n; K_s = Kc; vC = vN; vW = vWn;
     }
 
     // ---- fused diagnostics of the state at the start of the step --------------------------
@@ -459,7 +465,7 @@ __device__ __forceinline__ double thirdR(double xm, double x5, double x2) {     
 __device__ __forceinline__ double upwind_sel(double vel, double L, double Rr) { return vel * (vel > 0.0 ? L : Rr); }
 
 template <int STAGE, bool DIAG>
-__global__ void __launch_bounds__(NT, RB_MINB) substage_rbd_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem_bytes[];
     double *const s_u = reinterpret_cast<double *>(smem_bytes);
     double *const s_v = s_u + SZP, *const s_h = s_u + 2 * SZP, *const s_A = s_u + 3 * SZP;
