@@ -29,6 +29,9 @@ import sys
 import time
 from pathlib import Path
 
+# stdout carries exactly one JSON line: NCCL's version banner / debug output (NCCL_DEBUG set on the box) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
