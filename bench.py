@@ -29,8 +29,11 @@ import sys
 import time
 from pathlib import Path
 
-# stdout carries exactly one JSON line: NCCL's version banner / debug output (NCCL_DEBUG set on the box) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly one JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner when
+# NCCL_DEBUG is set on the box): the process's fd 1 is pointed at stderr and the JSON line goes to a
+# duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import numpy as np
 
@@ -187,7 +190,7 @@ def run_reference(args):
                          "sample": f"{args.steps} RK3 steps of a {Nx}x{rows} band, {cores} OpenMP threads"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -401,7 +404,7 @@ def run_native(args):
                    "all_finite": bool(finite)},
         "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if dist:
         dist.destroy_process_group()
 
