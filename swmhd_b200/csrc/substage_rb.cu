@@ -35,8 +35,8 @@ namespace {
 #ifndef RB_MINB            // CTAs per SM the Jacobian kernel is compiled for (<= 128 registers, 55.6 KB of shared memory)
 #define RB_MINB 4
 #endif
-#ifndef RB_MINB_D          // the divergence kernel: 71 KB of shared memory
-#define RB_MINB_D 3
+#ifndef RB_MINB_D          // the divergence kernel: 55.4 KB of shared memory
+#define RB_MINB_D 4
 #endif
 #ifndef RB_L2_PREFETCH
 #define RB_L2_PREFETCH 1
@@ -442,14 +442,12 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
 // a tile is 31 cells wide (32 faces), which costs 3 % of the lanes instead of a pre-pass over three
 // flux families.
 constexpr int TXD = TX - 1;                                // cells per tile row in the divergence kernel
-constexpr int BP = TX + 4, BR = TYB + 4;                   // hBx, hBy, Bx, By, 1/ℑx h, 1/ℑy h: a in [1,TX+4], b in [1,TYB+4]
-constexpr int HP = TX + 1, HR = TYB + 1;                   // 1/ℑxy h at ffc: a in [3,TX+3], b in [3,TYB+3]
+constexpr int BP = TX + 4, BR = TYB + 4;                   // hBx, hBy, Bx, By: a in [1,TX+4], b in [1,TYB+4]
 constexpr int RP = TX + 2, RR = TYB + 2;                   // 1/h at ccc: a in [2,TX+3], b in [2,TYB+3]
-constexpr int NB = BP * BR, NH = HP * HR, NRH = RP * RR;
-constexpr int DERIVED_D = 6 * NB + NH + NRH;
+constexpr int NB = BP * BR, NRH = RP * RR;
+constexpr int DERIVED_D = 4 * NB + NRH;                    // 55.4 KB with the raw tile: 4 CTAs per SM
 constexpr size_t SMEM_BYTES_D = ((size_t)4 * SZP + DERIVED_D + 2 + NW * NDIAG) * sizeof(double);
 #define Bf(arr, a, b) arr[((b) - 1) * BP + (a) - 1]
-#define RHF(a, b) s_rhff[((b) - 3) * HP + (a) - 3]
 #define RH(a, b) s_rh[((b) - 2) * RP + (a) - 2]
 
 __device__ __forceinline__ double sym4(double a, double b, double c, double d) {
@@ -471,8 +469,7 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
     double *const s_v = s_u + SZP, *const s_h = s_u + 2 * SZP, *const s_A = s_u + 3 * SZP;
     double *const smem = s_u + 4 * SZP;
     double *const s_hBx = smem, *const s_hBy = smem + NB, *const s_Bx = smem + 2 * NB, *const s_By = smem + 3 * NB;
-    double *const s_rhx = smem + 4 * NB, *const s_rhy = smem + 5 * NB;      // 1/ℑx h, 1/ℑy h
-    double *const s_rhff = smem + 6 * NB, *const s_rh = s_rhff + NH;        // 1/ℑxy h at ffc, 1/h at ccc
+    double *const s_rh = smem + 4 * NB;                                    // 1/h at ccc (each used by F_uu and F_vv)
     uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem + DERIVED_D);
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
     const int Nx = p.Nx, P = p.P;
@@ -524,23 +521,18 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
         const double hc = RAW(s_h, a, b);
         const double rhx = frcp(0.5 * (RAW(s_h, a - 1, b) + hc)), rhy = frcp(0.5 * (RAW(s_h, a, b - 1) + hc));
         s_hBx[t] = hbx; s_hBy[t] = hby;
-        s_rhx[t] = rhx; s_rhy[t] = rhy;
         s_Bx[t] = hbx * rhx; s_By[t] = hby * rhy;
     }
-    for (int t = tid; t < NH + NRH; t += NT) {
-        if (t < NH) {
-            const int a = 3 + t % HP, b = 3 + t / HP;
-            s_rhff[t] = frcp(avg4(RAW(s_h, a - 1, b - 1), RAW(s_h, a, b - 1), RAW(s_h, a - 1, b), RAW(s_h, a, b)));
-        } else {
-            const int q = t - NH, a = 2 + q % RP, b = 2 + q / RP;
-            s_rh[q] = frcp(RAW(s_h, a, b));
-        }
+    for (int q = tid; q < NRH; q += NT) {
+        const int a = 2 + q % RP, b = 2 + q / RP;
+        s_rh[q] = frcp(RAW(s_h, a, b));
     }
     __syncthreads();
 
     // ---- B/C: warp-private row walk ----------------------------------------------------------------------
     const double es = eps * (12.0 / 13.0);
     double Fvu_s = 0.0, Fvv_s = 0.0, Ty_s = 0.0, vq_s = 0.0;   // south side of the current row (from the previous iteration)
+    double rhff_s = 0.0;                                       // 1/ℑxy h at the ffc point (li, lj), likewise
     double dg[NDIAG];
     if constexpr (DIAG) {
 #pragma unroll
@@ -563,7 +555,7 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
             }
         }
         // ---- north side: F_vu - Lyx at ffc (li, ln), F_vv - Lyy at ccc (li, lj), tracer flux at cfc (li, ln) ----
-        double Fvu_n, Fvv_c, Ty_n, vq_n;
+        double Fvu_n, Fvv_c, Ty_n, vq_n, rhff_n;
         {
             const double vln = RAW(s_v, li, ln);
             double vel[3];
@@ -575,11 +567,21 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
             }
             vel[2] = vln;
             const double *const cu = &RAW(s_u, li, ln), *const cv = &RAW(s_v, li, ln), *const cA = &RAW(s_A, li, ln);
-            double d1[3], d2[3], d3[3], d4[3], c0[3] = {es, es, es}, c1[3] = {es, es, es}, c2[3] = {es, es, es}, num[3], den[3], rc[3], cc[3];
+            double d1[3], d2[3], d3[3], d4[3], c0[3] = {es, es, es}, c1[3] = {es, es, es}, c2[3] = {es, es, es}, num[3], den[3], cc[3];
             UPDC(vel[0] > 0.0, cu, W, 0, cc[0]); UPDC(vel[1] > 0.0, cv, W, 1, cc[1]); UPDC(vel[2] > 0.0, cA, W, 2, cc[2]);
             beta_acc_n<3>(d1, d2, d3, d4, c0, c1, c2);
             corr_n<3>(d1, d2, d3, d4, c0, c1, c2, num, den);
-            rcp_n<3>(den, rc);
+            // the three WENO denominators and the face depths ℑy h at cfc (li, ln), ℑxy h at ffc (li, ln): five reciprocals together
+            double x5[5], rc[5];
+            {
+                const double h00 = RAW(s_h, li, lj), h01 = RAW(s_h, li, ln);
+                x5[0] = den[0]; x5[1] = den[1]; x5[2] = den[2];
+                x5[3] = 0.5 * (h00 + h01);
+                x5[4] = avg4(RAW(s_h, li - 1, lj), h00, RAW(s_h, li - 1, ln), h01);
+            }
+            rcp_n<5>(x5, rc);
+            const double rhy_n = rc[3];
+            rhff_n = rc[4];
             double fl[3];
 #pragma unroll
             for (int n = 0; n < 3; n++) fl[n] = vel[n] * fma(num[n], rc[n], cc[n]);
@@ -587,7 +589,7 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
             if (ybuf(by, gj + 1, 3, NyG)) { fl[0] = vel[0] * sym2(cu[-W], cu[0]); fl[2] = vel[2] * sym2(cA[-W], cA[0]); }
             if (ybuf(by, gj + 1, 3, NyG + 1)) fl[1] = vel[1] * sym2(cv[-W], cv[0]);
             {   // F_vu - Lyx (advective_lorentz_flux_hBy_bx, :62-84 with its edge branches)
-                const double mom = (p.dx * fl[0]) * RHF(li, ln);
+                const double mom = (p.dx * fl[0]) * rhff_n;
                 const double vl = 0.5 * (Bf(s_hBy, li - 1, ln) + Bf(s_hBy, li, ln));
                 const double B0 = Bf(s_Bx, li, ln), Bm = Bf(s_Bx, li, ln - 1);
                 const double L3 = third(B0, Bm, Bf(s_Bx, li, ln - 2)), R3 = thirdR(Bf(s_Bx, li, ln + 1), B0, Bm);
@@ -612,9 +614,8 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                 Fvv_c = p.dx * upwind_sel(vl, Lq, Rq) - mom;
             }
             {   // tracer transport flux and vh/ℑy h at cfc (li, ln)
-                const double rhy = Bf(s_rhy, li, ln);
-                Ty_n = (p.dx * fl[2]) * rhy;
-                vq_n = vln * rhy;
+                Ty_n = (p.dx * fl[2]) * rhy_n;
+                vq_n = vln * rhy_n;
             }
         }
         if (it >= 0) {
@@ -630,11 +631,12 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                 }
                 vel[2] = uc;
                 const double *const cu = &RAW(s_u, li, lj), *const cv = &RAW(s_v, li, lj), *const cA = &RAW(s_A, li, lj);
-                double d1[3], d2[3], d3[3], d4[3], c0[3] = {es, es, es}, c1[3] = {es, es, es}, c2[3] = {es, es, es}, num[3], den[3], rc[3], cc[3];
+                double d1[3], d2[3], d3[3], d4[3], c0[3] = {es, es, es}, c1[3] = {es, es, es}, c2[3] = {es, es, es}, num[3], den[3], cc[3];
                 UPDC(vel[0] > 0.0, cu, 1, 0, cc[0]); UPDC(vel[1] > 0.0, cv, 1, 1, cc[1]); UPDC(vel[2] > 0.0, cA, 1, 2, cc[2]);
                 beta_acc_n<3>(d1, d2, d3, d4, c0, c1, c2);
                 corr_n<3>(d1, d2, d3, d4, c0, c1, c2, num, den);
-                rcp_n<3>(den, rc);
+                double x4[4] = {den[0], den[1], den[2], 0.5 * (RAW(s_h, li - 1, lj) + RAW(s_h, li, lj))}, rc[4];   // + ℑx h at fcc (li, lj)
+                rcp_n<4>(x4, rc);
                 double fl[3];
 #pragma unroll
                 for (int n = 0; n < 3; n++) fl[n] = vel[n] * fma(num[n], rc[n], cc[n]);
@@ -646,14 +648,14 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                     Fuu_w = p.dy * upwind_sel(ul, Lq, Rq) - mom;
                 }
                 {   // F_uv - Lxy (advective_lorentz_flux_hBx_by, :86-108) at the ffc point (li, lj)
-                    const double mom = (p.dy * fl[1]) * RHF(li, lj);
+                    const double mom = (p.dy * fl[1]) * rhff_s;
                     const double ul = 0.5 * (Bf(s_hBx, li, lj - 1) + Bf(s_hBx, li, lj));
                     const double B0 = Bf(s_By, li, lj), Bm = Bf(s_By, li - 1, lj);
                     const double Lq = third(B0, Bm, Bf(s_By, li - 2, lj)), Rq = thirdR(Bf(s_By, li + 1, lj), B0, Bm);
                     Fuv_w = p.dy * upwind_sel(ul, Lq, Rq) - mom;
                 }
                 {   // tracer transport flux and uh/ℑx h at fcc (li, lj)
-                    const double rhx = Bf(s_rhx, li, lj);
+                    const double rhx = rc[3];
                     Tx_w = (p.dy * fl[2]) * rhx;
                     uq_w = uc * rhx;
                 }
@@ -702,7 +704,7 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                 }
             }
         }
-        Fvu_s = Fvu_n; Fvv_s = Fvv_c; Ty_s = Ty_n; vq_s = vq_n;
+        Fvu_s = Fvu_n; Fvv_s = Fvv_c; Ty_s = Ty_n; vq_s = vq_n; rhff_s = rhff_n;
     }
 
     // ---- fused diagnostics of the state at the start of the step ------------------------------
@@ -710,16 +712,25 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
         double *const s_red = smem + DERIVED_D + 2;
         constexpr int NR = R + 2;                            // rows b = lj0-1 .. lj0+R, index k = b - (lj0-1)
         auto sq = [](double x) { return x * x; };
-        double Ac[NR], Aw[NR], Ae[NR], sqy[NR], sqx[NR];
+        double Ac[NR], Aw[NR], Ae[NR], sqy[NR], sqx[NR], rhx[NR];
+        {
+            double den[2 * NR - 1], rc[2 * NR - 1], hcol[NR];
 #pragma unroll
-        for (int k = 0; k < NR; k++) {
-            const int b = lj0 - 1 + k;
-            Ac[k] = RAW(s_A, li, b); Aw[k] = RAW(s_A, li - 1, b); Ae[k] = RAW(s_A, li + 1, b);
-            sqy[k] = sq(((Ac[k] - Aw[k]) * p.rdx) * Bf(s_rhx, li, b));                       // (dxA / ℑx h)^2 at fcc
+            for (int k = 0; k < NR; k++) {
+                const int b = lj0 - 1 + k;
+                Ac[k] = RAW(s_A, li, b); Aw[k] = RAW(s_A, li - 1, b); Ae[k] = RAW(s_A, li + 1, b);
+                hcol[k] = RAW(s_h, li, b);
+                den[k] = 0.5 * (RAW(s_h, li - 1, b) + hcol[k]);                              // ℑx h at fcc(li, b)
+            }
+#pragma unroll
+            for (int k = 1; k < NR; k++) den[NR + k - 1] = 0.5 * (hcol[k - 1] + hcol[k]);     // ℑy h at cfc(li, b)
+            rcp_n<2 * NR - 1>(den, rc);
+#pragma unroll
+            for (int k = 0; k < NR; k++) { rhx[k] = rc[k]; sqy[k] = sq(((Ac[k] - Aw[k]) * p.rdx) * rc[k]); }   // (dxA / ℑx h)^2 at fcc
+            sqx[0] = 0.0;
+#pragma unroll
+            for (int k = 1; k < NR; k++) sqx[k] = sq(-((Ac[k] - Ac[k - 1]) * p.rdy) * rc[NR + k - 1]);          // (dyA / ℑy h)^2 at cfc
         }
-        sqx[0] = 0.0;
-#pragma unroll
-        for (int k = 1; k < NR; k++) sqx[k] = sq(-((Ac[k] - Ac[k - 1]) * p.rdy) * Bf(s_rhy, li, lj0 - 1 + k));   // (dyA / ℑy h)^2 at cfc
         double uu[R], vc[R + 1], kb[R];
         {
             double vw2[R + 1], vc2[R + 1];
@@ -749,7 +760,7 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                 const double dh = hh - p.h_ref;
                 dg[2] += (0.5 * p.g) * (dh * dh);
                 dg[3] += hh;
-                dg[4] = fmax(dg[4], fabs(uu[r] * Bf(s_rhx, li, lj)));
+                dg[4] = fmax(dg[4], fabs(uu[r] * rhx[k]));
                 dg[5] = fmax(dg[5], fabs(aa));
                 dg[6] = fmax(dg[6], -hh);
                 {
