@@ -1,22 +1,27 @@
-// substage_rb.cu — row-blocked fused RK3-substage kernel (sm_100a), Jacobian formulation, FAST arithmetic.
+// substage_rb.cu — row-blocked fused RK3-substage kernels (sm_100a), FAST arithmetic, both formulations.
 //
 // Same work per launch as substage_kernel.cu (calculate_tendencies! + rk3_substep! + store_tendencies!
-// for all four fields, jacobian_formulation/sw_mhd_jacobian_functions.jl:1-26 inlined; in the
-// stage-1 DIAG variant also the diagnostics of SWMHD_example.jl:47-77), different thread mapping:
+// for all four fields with the reference's Lorentz closures inlined — substage_rb_kernel:
+// jacobian_formulation/sw_mhd_jacobian_functions.jl:1-26; substage_rbd_kernel:
+// divergence_formulation/sw_mhd_divergence_functions.jl:1-170 — and in the stage-1 DIAG variants the
+// diagnostics of SWMHD_example.jl:47-77 / divergence_sw_mhd.jl:42-75), different thread mapping:
 //
 //   * a CTA owns a 32 x RB_TY tile staged by TMA, a WARP owns RB_R consecutive rows of it and walks
 //     them south to north, a THREAD one column of those rows.
-//   * after the derived staggered fields (phase A, CTA-wide) warps never meet again: the flux through
-//     a cell's north face is kept in registers for the next row (one extra evaluation per warp for the
-//     south face of its first row), the east-face fluxes travel by warp shuffle, the tile's east column
-//     of faces is a per-warp pre-pass.  One __syncthreads per tile (one more in the DIAG variant)
-//     instead of three, and no flux arrays in shared memory.
+//   * after the derived staggered fields (phase A, CTA-wide) warps never meet again: the fluxes through
+//     a cell's north face are kept in registers for the next row (one extra evaluation per warp for the
+//     south face of its first row), the east-face fluxes travel by warp shuffle (Jacobian: the tile's
+//     east column of faces is a per-warp pre-pass; divergence: lane 31 only supplies them).
+//     One __syncthreads per tile (one more in the DIAG variants) instead of three, no flux arrays.
+//   * phase A keeps only what several threads share and what is expensive: anything a thread can rebuild
+//     from values it holds anyway (kinetic energy, reciprocals of face depths) stays in registers, so that
+//     the tile fits four times into an SM (55 KB of shared memory, <= 128 registers: 16 warps per SM).
 //   * the next tile of the SM slot is pulled into L2 while this one computes (cp.async.bulk.prefetch).
 //
-// Measured (profiles/README.md): 0.67 / 0.72 / 0.70 ms per stage at 4096^2 against 0.756 / 0.782 /
-// 0.743 ms of the one-thread-per-cell kernel; with the fused diagnostics 0.84 vs 1.06 ms.  A variant
-// that also kept the y stencils in sliding register windows was slower (register moves and selects
-// outweighed the saved shared-memory loads): see the history table there.
+// Measured at 4096^2 (profiles/README.md): Jacobian 0.67 / 0.71 / 0.70 ms per stage against 0.756 / 0.782 /
+// 0.743 ms of the one-thread-per-cell kernel, divergence 0.74 / 0.77 / 0.76 against 0.93 / 0.94 / 0.88 ms.
+// Variants that were measured and dropped (y stencils in sliding register windows, unrolled row loop, other
+// tile shapes) are in the history table there.
 // Arithmetic per value is the FAST arithmetic of substage_kernel.cu (same operation order).
 #include "kparams.h"
 #include "device_prims.cuh"
