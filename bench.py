@@ -310,7 +310,7 @@ def run_native(args):
             ctx.close()
             e2e = None
     else:
-        from swmhd_b200.distributed import SlabModel, split_rows
+        from swmhd_b200.distributed import SlabModel, split_rows, run_in_step_for
         j0, ny = split_rows(NyG, world)[rank]
         # slab ICs straight from the closed forms at this slab's nodes (halo rows come from the exchange)
         gridl = RectilinearGrid((Nx, ny), (-Lx / 2, Lx / 2), (-Ly / 2 + j0 * (Ly / NyG), -Ly / 2 + (j0 + ny) * (Ly / NyG)), topology=topo)
@@ -322,9 +322,12 @@ def run_native(args):
         sm.synchronize()
         if sampler:
             sampler.start()
-        t_s = time.perf_counter()
-        while time.perf_counter() - t_s < 1.5:       # same untimed load on every rank while nvidia-smi starts
+        # same untimed load on every rank while nvidia-smi starts; every rank runs the same number of steps
+        # (rank 0's clock decides: a slab step exchanges halo rows, uneven counts would dead-lock)
+        def _warm():
             sm.step(dt, 2)
+            sm.synchronize()
+        run_in_step_for(1.5, _warm, f"cuda:{local}")
         sm.synchronize()
         dist.barrier(); torch.cuda.synchronize()
         l0 = sm.ctx.launch_count

@@ -98,6 +98,23 @@ def self_exchange(rows_of):
         rows_of(f, NORTH_HALO).copy_(rows_of(f, SOUTH_SEND))
 
 
+def run_in_step_for(seconds: float, step, device, clock=None) -> int:
+    """Call step() repeatedly for about `seconds` of RANK 0's wall clock and return the number of calls,
+    the SAME on every rank.  A slab step exchanges halo rows with its neighbours, so ranks that left a
+    time-based loop after different numbers of steps would dead-lock: rank 0 decides, the others follow."""
+    import time
+    clock = clock or time.perf_counter
+    t_s = clock()
+    go = torch.ones(1, dtype=torch.int32, device=device)
+    n = 0
+    while int(go.item()):
+        step()
+        n += 1
+        go.fill_(1 if clock() - t_s < seconds else 0)
+        dist.broadcast(go, src=0)
+    return n
+
+
 @dataclass
 class SlabTimings:
     ms: float = 0.0

@@ -82,3 +82,39 @@ def test_slab_exchange_matches_single_domain(world, kind):
     for p in procs:
         p.join(timeout=60)
     assert all(ok and hok for _, ok, hok in res), res
+
+
+def _warm_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import time
+        from swmhd_b200 import distributed as D
+        # skewed clocks: rank 1 believes much more time has passed than rank 0
+        skew = 10.0 * rank
+        t = torch.zeros(1)
+
+        def step():                       # a "step" that needs every rank (like the halo exchange)
+            dist.all_reduce(t)
+            time.sleep(0.01)
+
+        n = D.run_in_step_for(0.2, step, "cpu", clock=lambda: time.perf_counter() + skew * (time.perf_counter() % 1.0))
+        q.put((rank, n))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_boxed_loop_runs_the_same_number_of_steps_on_every_rank():
+    """bench.py keeps the GPUs busy for ~1.5 s before timing; the ranks must agree on the step count."""
+    world, port = 3, 29731
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_warm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(set(res.values())) == 1 and res[0] >= 1, res
