@@ -23,8 +23,11 @@
  * SURVEY.md Appendix A, and is pinned only by
  *   (i)   the closed-form answers of the reference's own operator scripts
  *         (test_formulations.jl:12-18, MHD_visualize.jl:8-24),
- *   (ii)  the reference's published energy traces digitised to +-1e-5
- *         (energy_plots/), and
+ *   (ii)  all twelve published energy plots of the reference (energy_plots/:
+ *         3 initial conditions x 64^2/128^2 x both formulations, Bounded-y
+ *         included), machine-digitised every half time unit into
+ *         tests/golden/published_traces.json: 1e-5 absolute in the low-B
+ *         runs, 0.1-0.4 % in the others (tests/test_published_traces.py), and
  *   (iii) the survey's independent scratch-restatement checksums (B.5).
  * julia/dump_reference.jl writes real-upstream golden files wherever Julia +
  * Oceananigans exist.
