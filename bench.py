@@ -32,8 +32,11 @@ from pathlib import Path
 # stdout carries exactly one JSON line.  Libraries print there too (NCCL's "NCCL version ..." banner when
 # NCCL_DEBUG is set on the box): the process's fd 1 is pointed at stderr and the JSON line goes to a
 # duplicate of the original stdout.
-_JSON_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+try:
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+except OSError:                     # no usable stderr / stdout descriptors: print the JSON line the plain way
+    _JSON_OUT = sys.stdout
 
 import numpy as np
 
