@@ -565,7 +565,6 @@ __global__ void __launch_bounds__(NT, SWMHD_MINB) substage_kernel(const __grid_c
         __syncthreads();
 
         // ---- P1b: every flux once --------------------------------------------------------
-        constexpr int NXF = XP * XR, NYF = YP * YR;
         constexpr int NDG = DIAG ? NDG_ : 0;
         const int NyG = p.NyG, by = p.by;
         // Six flux families, one WENO5 each.  Every thread evaluates the six fluxes anchored at its own
