@@ -14,7 +14,7 @@ SRC = (ROOT / "swmhd_b200" / "csrc" / "substage_rb.cu").read_text()
 
 def _kernels():
     from swmhd_b200 import build
-    build.build()                                   # no-op when the library is up to date
+    build.build(force=not LOG.exists())             # no-op when the library is up to date and its log is there
     text = LOG.read_text()
     out = {}
     for m in re.finditer(r"Compiling entry function '(\S+)'.*?(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads.*?Used (\d+) registers",
