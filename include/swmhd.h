@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SWMHD_ABI_VERSION 1
+#define SWMHD_ABI_VERSION 2
 
 enum {
     SWMHD_OK              =  0,
@@ -43,8 +43,10 @@ enum {
     SWMHD_ERR_CUDA        = -2,  /* CUDA runtime error (see swmhd_last_error) */
     SWMHD_ERR_NONFINITE   = -3,  /* state contains NaN/Inf                    */
     SWMHD_ERR_NODEVICE    = -4,  /* no CUDA device: there is no CPU fallback  */
-    SWMHD_ERR_STATE       = -5   /* call sequence error                       */
+    SWMHD_ERR_STATE       = -5,  /* call sequence error                       */
+    SWMHD_ERR_NCCL        = -6   /* NCCL error / libnccl.so.2 not loadable    */
 };
+#define SWMHD_MAX_GPUS 8
 
 enum { SWMHD_PERIODIC = 0, SWMHD_BOUNDED = 1 };
 
@@ -97,6 +99,15 @@ typedef struct swmhd_config {
        stored exactly like a (Nx, slab_ny) Field with Hy=3 halos.             */
     int32_t slab_j0, slab_ny;
     int32_t rank, world;   /* position of the slab in the y ring              */
+    /* Single-process multi-GPU: n_gpus > 1 (then world must be 1, slab_j0 = 0,
+       slab_ny = Ny).  The context splits the Ny rows into n_gpus y-slabs, one
+       per device in device_ids[] (south to north), creates one NCCL
+       communicator per device (ncclCommInitAll) and exchanges the halo rows
+       itself; host buffers of set/get are the GLOBAL parent arrays.
+       n_gpus = 0 or 1: one GPU (`device`).                                   */
+    int32_t n_gpus;
+    int32_t device_ids[SWMHD_MAX_GPUS];
+    int32_t reserved0;
 } swmhd_config;
 
 typedef struct swmhd_diag {
@@ -127,8 +138,11 @@ size_t swmhd_field_len(const swmhd_ctx *ctx, int field);  /* doubles in the pare
 /* update_state!(model) = fill_halo_regions! on solution and tracers (after set!) */
 int  swmhd_fill_halos(swmhd_ctx *ctx);
 
-/* time_step!(model, dt) x nsteps with RungeKutta3 — SWMHD_example.jl:23,42,97.
-   Single-slab contexts only (world == 1). Blocking. */
+/* time_step!(model, dt) x nsteps with RungeKutta3 — SWMHD_example.jl:23,42,97.  Blocking.
+   Valid for one GPU, for n_gpus > 1 (single process) and for world > 1 once swmhd_comm_init has
+   been called (one process per GPU; every rank makes the same calls): per substage the rows within
+   one tile of a slab edge run first on a high-priority stream, their halo rows travel by
+   ncclSend/ncclRecv (one group per substage) while the interior runs on the main stream. */
 int  swmhd_step(swmhd_ctx *ctx, double dt, int nsteps);
 /* same, but diagnostics of the state at the START of each step are produced by
    the stage-1 kernel at no extra HBM traffic and written to diags[0..nsteps) */
@@ -136,7 +150,9 @@ int  swmhd_step_diag(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags);
 
 /* one RK3 substage (stage = 1,2,3), including the halo fill that follows it */
 int  swmhd_substage(swmhd_ctx *ctx, double dt, int stage);
-/* calculate_tendencies!(model): G^n of the current state into four host parent arrays */
+/* calculate_tendencies!(model): G^n of the current state into four host parent arrays, each of
+   capacity n_each doubles (>= the longest field: v|vh has one row more in a Bounded-y grid).
+   Single slab, between steps only (SWMHD_ERR_STATE after stage 1 or 2 of a step: it overwrites G^-). */
 int  swmhd_tendencies(swmhd_ctx *ctx, double *const G_host[4], size_t n_each);
 
 /* the four energy means and the progress-callback reductions —
@@ -146,18 +162,40 @@ int  swmhd_diagnostics(swmhd_ctx *ctx, swmhd_diag *out);
 /* The field writer's outputs (SWMHD_example.jl:67-69,81-84; divergence_sw_mhd.jl:63-66,77-82) computed on
    the device: u, v (velocities; uh/Ix(h), vh/Iy(h) for DIVERGENCE) and s = sqrt(u^2 + v^2) at (Face, Center),
    as parent arrays of u-, v- and u-shaped fields (halos filled).  A is swmhd_get_field(ctx, SWMHD_A).
-   Call between steps only (it stages through the tendency buffers). */
+   Call between steps only (it stages through the tendency buffers). Blocking. */
 int  swmhd_get_outputs(swmhd_ctx *ctx, double *u_host, double *v_host, double *s_host);
+/* The same writer (JLD2OutputWriter(model, (; u, v, A, s), schedule = TimeInterval(0.1)),
+   SWMHD_example.jl:81-84; with_halos = true, divergence_sw_mhd.jl:79) without stalling the step loop:
+   u, v, s and A of the CURRENT state are computed into staging buffers owned by the context and
+   copied to the four host parent arrays on a copy stream; the call returns once that work is queued
+   and swmhd_step may be called right away.  The host arrays are valid after swmhd_outputs_wait.
+   For a truly asynchronous copy the host arrays must be page-locked (swmhd_pin_host). */
+int  swmhd_get_outputs_async(swmhd_ctx *ctx, double *u_host, double *v_host, double *s_host, double *A_host);
+int  swmhd_outputs_wait(swmhd_ctx *ctx);
+int  swmhd_pin_host(void *ptr, size_t bytes);     /* cudaHostRegister / cudaHostUnregister */
+int  swmhd_unpin_host(void *ptr);
 
 /* model.clock: time and iteration as advanced by the RK3 stages */
 double  swmhd_time(const swmhd_ctx *ctx);
 int64_t swmhd_iteration(const swmhd_ctx *ctx);
 int  swmhd_set_clock(swmhd_ctx *ctx, double time, int64_t iteration);
 
-/* ---- y-slab (multi-GPU) plumbing: one context per process per GPU ---------
-   The host owns the exchange (NCCL send/recv via torch.distributed, or MPI in
-   Julia).  Per substage:  swmhd_substage_edges -> exchange rows ->
-   swmhd_substage_interior -> swmhd_substage_finish.                          */
+/* ---- y-slabs, one process per GPU (world > 1) ----------------------------------------------
+   Rank 0 obtains an NCCL unique id, the host side distributes it (torch.distributed / MPI
+   broadcast: plumbing), and every rank hands it to its context: swmhd_comm_init is collective
+   (ncclCommInitRank(world, id, rank)).  From then on swmhd_fill_halos, swmhd_step[_diag],
+   swmhd_substage and swmhd_diagnostics run the halo exchange and the cross-rank reductions
+   inside the library.  libnccl.so.2 is dlopen'ed on first use (SWMHD_NCCL_LIB overrides the
+   name), so a single-GPU user does not need NCCL. */
+#define SWMHD_COMM_ID_BYTES 128
+int  swmhd_comm_unique_id(void *id, size_t nbytes);                 /* nbytes >= SWMHD_COMM_ID_BYTES */
+int  swmhd_comm_init(swmhd_ctx *ctx, const void *id, size_t nbytes);
+/* (first row, rows) of slab `index` of `nslabs` for a grid of Ny rows: the decomposition used by n_gpus > 1 */
+int  swmhd_split_rows(int Ny, int nslabs, int index, int *j0, int *ny);
+
+/* ---- host-driven exchange (legacy: a host that owns its own transport, e.g. MPI in Julia) ----
+   Per substage:  swmhd_substage_edges -> exchange rows -> swmhd_substage_interior ->
+   swmhd_substage_finish.  Contexts with world > 1 and no swmhd_comm_init only.              */
 int  swmhd_set_streams(swmhd_ctx *ctx, void *main_stream, void *edge_stream);
 int  swmhd_substage_edges(swmhd_ctx *ctx, double dt, int stage);    /* rows within 3 of a slab edge  */
 int  swmhd_substage_interior(swmhd_ctx *ctx, double dt, int stage); /* the rest, on the main stream   */

@@ -9,9 +9,11 @@ import ctypes as C
 import os
 from pathlib import Path
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
-OK, ERR_ARG, ERR_CUDA, ERR_NONFINITE, ERR_NODEVICE, ERR_STATE = 0, -1, -2, -3, -4, -5
+OK, ERR_ARG, ERR_CUDA, ERR_NONFINITE, ERR_NODEVICE, ERR_STATE, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
+MAX_GPUS = 8
+COMM_ID_BYTES = 128
 PERIODIC, BOUNDED = 0, 1
 JACOBIAN, DIVERGENCE = 0, 1
 U, V, H, A = 0, 1, 2, 3
@@ -39,6 +41,7 @@ class Config(C.Structure):
         ("A_grad_south", C.c_double), ("A_grad_north", C.c_double),
         ("slab_j0", C.c_int32), ("slab_ny", C.c_int32),
         ("rank", C.c_int32), ("world", C.c_int32),
+        ("n_gpus", C.c_int32), ("device_ids", C.c_int32 * MAX_GPUS), ("reserved0", C.c_int32),
     ]
 
 
@@ -57,7 +60,7 @@ class Diag(C.Structure):
 
 def make_config(Nx, Ny, Lx=10.0, Ly=10.0, formulation=JACOBIAN, topo_y=PERIODIC, g=9.81, f=1.0,
                 arith=ARITH_FAST, flags=0, weno_eps=1e-6, h_ref=1.0, A_gradient=None, device=0,
-                slab_j0=0, slab_ny=None, rank=0, world=1) -> Config:
+                slab_j0=0, slab_ny=None, rank=0, world=1, device_ids=None) -> Config:
     c = Config()
     c.abi_version = ABI_VERSION
     c.Nx, c.Ny, c.Hx, c.Hy = Nx, Ny, HALO, HALO
@@ -72,6 +75,11 @@ def make_config(Nx, Ny, Lx=10.0, Ly=10.0, formulation=JACOBIAN, topo_y=PERIODIC,
     c.slab_j0 = slab_j0
     c.slab_ny = Ny if slab_ny is None else slab_ny
     c.rank, c.world = rank, world
+    if device_ids is not None and len(device_ids) > 1:      # single-process multi-GPU: one y-slab per device
+        c.n_gpus = len(device_ids)
+        for i, d in enumerate(device_ids):
+            c.device_ids[i] = d
+        c.device = device_ids[0]
     return c
 
 
@@ -93,6 +101,13 @@ SYMBOLS = [
     ("swmhd_tendencies", C.c_int, [_ctx, C.POINTER(_dp), C.c_size_t]),
     ("swmhd_diagnostics", C.c_int, [_ctx, C.POINTER(Diag)]),
     ("swmhd_get_outputs", C.c_int, [_ctx, _dp, _dp, _dp]),
+    ("swmhd_get_outputs_async", C.c_int, [_ctx, _dp, _dp, _dp, _dp]),
+    ("swmhd_outputs_wait", C.c_int, [_ctx]),
+    ("swmhd_pin_host", C.c_int, [C.c_void_p, C.c_size_t]),
+    ("swmhd_unpin_host", C.c_int, [C.c_void_p]),
+    ("swmhd_comm_unique_id", C.c_int, [C.c_void_p, C.c_size_t]),
+    ("swmhd_comm_init", C.c_int, [_ctx, C.c_void_p, C.c_size_t]),
+    ("swmhd_split_rows", C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("swmhd_time", C.c_double, [_ctx]),
     ("swmhd_iteration", C.c_int64, [_ctx]),
     ("swmhd_set_clock", C.c_int, [_ctx, C.c_double, C.c_int64]),

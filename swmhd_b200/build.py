@@ -28,11 +28,12 @@ UNITS = [
     ("substage_rb.cu", "substage_rb.o", []),
     ("aux_kernels.cu", "aux_kernels.o", []),
     ("swmhd_api.cu", "swmhd_api.o", []),
+    ("nccl_dyn.cpp", "nccl_dyn.o", []),
 ]
 
 
 def _deps():
-    return list(CSRC.glob("*.cu")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "swmhd.h"]
+    return list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "swmhd.h"]
 
 
 def needs_build() -> bool:
@@ -58,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(exist_ok=True)
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(_compile, UNITS))
-    cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *[str(OBJ / o) for o in objs], "-cudart", "static"]
+    cmd = [NVCC, *ARCH, "-shared", "-o", str(LIB), *[str(OBJ / o) for o in objs], "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -53,6 +53,7 @@ class Context:
 
     # -- fields -----------------------------------------------------------------------------
     def field_shape(self, field):
+        """(rows, pitch) of the host parent array: this slab's rows, or the global array for n_gpus > 1."""
         n = self.lib.swmhd_field_len(self._h, field)
         return (n // self.pitch, self.pitch)
 
@@ -101,7 +102,7 @@ class Context:
     def tendencies(self):
         G = [self.new_parent(k) for k in range(4)]
         arr = (_dp * 4)(*[_ptr(g) for g in G])
-        self._ck(self.lib.swmhd_tendencies(self._h, arr, G[0].size))
+        self._ck(self.lib.swmhd_tendencies(self._h, arr, max(g.size for g in G)))
         return G
 
     def diagnostics(self, check_finite=True) -> dict:
@@ -117,6 +118,26 @@ class Context:
         u, v, s = self.new_parent(abi.U), self.new_parent(abi.V), self.new_parent(abi.U)
         self._ck(self.lib.swmhd_get_outputs(self._h, _ptr(u), _ptr(v), _ptr(s)))
         return u, v, s
+
+    def get_outputs_async(self, u, v, s, A):
+        """Queue the field writer's outputs (u, v, s, A of the current state) into four host parent arrays
+        (page-locked for a truly asynchronous copy) and return; valid after outputs_wait()."""
+        self._ck(self.lib.swmhd_get_outputs_async(self._h, _ptr(u), _ptr(v), _ptr(s), _ptr(A)))
+
+    def outputs_wait(self):
+        self._ck(self.lib.swmhd_outputs_wait(self._h))
+
+    # -- NCCL ring (world > 1, one process per GPU) --------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(abi.COMM_ID_BYTES)
+        rc = self.lib.swmhd_comm_unique_id(buf, abi.COMM_ID_BYTES)
+        if rc != abi.OK:
+            raise SwmhdError(rc, (self.lib.swmhd_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init(self, uid: bytes):
+        buf = C.create_string_buffer(uid, abi.COMM_ID_BYTES)
+        self._ck(self.lib.swmhd_comm_init(self._h, buf, abi.COMM_ID_BYTES))
 
     # -- clock ------------------------------------------------------------------------------
     @property

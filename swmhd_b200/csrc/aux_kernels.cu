@@ -130,8 +130,9 @@ __global__ void __launch_bounds__(DT) diag_kernel(const DiagParams p) {
 // Fixed-order two-level final reduction (deterministic for a given launch geometry): block b folds
 // the contiguous chunk b of the per-tile partials (thread-strided, then a fixed binary tree) into
 // stage[b]; the last block to finish folds stage[0..FB) the same way.  Slots 4..7 are maxima.
+// The ticket counter of the "last block folds" pattern is owned by the CONTEXT (one word behind its
+// stage[] scratch, zeroed at create): two contexts reducing concurrently on one GPU never share it.
 constexpr int FT = 256, FB = 64;
-__device__ unsigned int g_final_ticket = 0;
 
 __device__ __forceinline__ void block_fold(double (&v)[NDIAG], double (*sh)[FT]) {
 #pragma unroll
@@ -149,7 +150,7 @@ __device__ __forceinline__ void block_fold(double (&v)[NDIAG], double (*sh)[FT])
     }
 }
 
-__global__ void __launch_bounds__(FT) diag_final_kernel(const double *partials, int nblocks, double *stage, double *out) {
+__global__ void __launch_bounds__(FT) diag_final_kernel(const double *partials, int nblocks, double *stage, double *out, unsigned int *ticket) {
     __shared__ double sh[NDIAG][FT];
     __shared__ bool last;
     const int per = (nblocks + FB - 1) / FB;
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(FT) diag_final_kernel(const double *partials, 
     if (threadIdx.x < NDIAG) stage[(size_t)blockIdx.x * NDIAG + threadIdx.x] = sh[threadIdx.x][0];
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(&g_final_ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!last) return;
     __threadfence();
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(FT) diag_final_kernel(const double *partials, 
     }
     block_fold(v, sh);
     if (threadIdx.x < NDIAG) out[threadIdx.x] = sh[threadIdx.x][0];
-    if (threadIdx.x == 0) g_final_ticket = 0;
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -227,16 +228,19 @@ int diag_blocks(int Nx, int Ny) {
     return (int)(n < 148 * 8 ? n : 148 * 8);
 }
 
+// stage[] = FB x NDIAG partials + one word for the ticket counter (must be zero before the first launch)
+int diag_stage_doubles() { return FB * NDIAG + 1; }
+static unsigned int *diag_ticket(double *stage) { return reinterpret_cast<unsigned int *>(stage + FB * NDIAG); }
+
 cudaError_t launch_diag(const DiagParams &p, double *out9, cudaStream_t st) {
     diag_kernel<<<p.nblocks, DT, 0, st>>>(p);
-    diag_final_kernel<<<FB, FT, 0, st>>>(p.partials, p.nblocks, p.stage, out9);
+    diag_final_kernel<<<FB, FT, 0, st>>>(p.partials, p.nblocks, p.stage, out9, diag_ticket(p.stage));
     return cudaGetLastError();
 }
 
-int diag_stage_doubles() { return FB * NDIAG; }
 
 cudaError_t launch_diag_final(const double *partials, int nblocks, double *stage, double *out9, cudaStream_t st) {
-    diag_final_kernel<<<FB, FT, 0, st>>>(partials, nblocks, stage, out9);
+    diag_final_kernel<<<FB, FT, 0, st>>>(partials, nblocks, stage, out9, diag_ticket(stage));
     return cudaGetLastError();
 }
 

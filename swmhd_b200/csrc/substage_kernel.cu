@@ -858,26 +858,32 @@ cudaError_t launch_cfg(const KParams &p, cudaStream_t st) {
     constexpr int NSTG = (TMA && FORM == 0) ? 2 : 1;
     constexpr size_t bytes = 128 + ((size_t)NSTG * 4 * SZP + SmemLayout<FORM, DIAG>::total) * sizeof(double) + 16;
     auto kern = substage_kernel<FORM, STAGE, DIAG, TMA, NSTG>;
-    static int max_ctas = 0;
-    if (max_ctas == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // per device (the shared-memory opt-in is a per-device attribute; a process may drive several devices)
+    constexpr int MAX_DEVICES = 64;
+    static int max_ctas_dev[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    if (max_ctas_dev[dev] == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, occ = 0;
-        cudaGetDevice(&dev);
+        int sms = 0, occ = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, bytes);
         if (e != cudaSuccess) return e;
         if (occ < 1) occ = 1;
-        max_ctas = occ * sms;
+        max_ctas_dev[dev] = occ * sms;
     }
+    const int max_ctas = max_ctas_dev[dev];
     const int ntiles = ((p.Nx + TX - 1) / TX) * p.tile_rows;
     static int tpc = -1;
-    if (tpc < 0) { const char *e = getenv("SWMHD_TPC"); tpc = e ? atoi(e) : SWMHD_TPC_DEFAULT; if (tpc < 1) tpc = 1; }
+    if (tpc < 0) { const char *ev = getenv("SWMHD_TPC"); tpc = ev ? atoi(ev) : SWMHD_TPC_DEFAULT; if (tpc < 1) tpc = 1; }
     KParams q = p;
     q.tiles_per_cta = (NSTG == 2) ? tpc : 1;
     const int grid = (ntiles + q.tiles_per_cta - 1) / q.tiles_per_cta;
     static int ahead = -2;
-    if (ahead == -2) { const char *e = getenv("SWMHD_L2_AHEAD"); ahead = e ? atoi(e) : -1; }
+    if (ahead == -2) { const char *ev = getenv("SWMHD_L2_AHEAD"); ahead = ev ? atoi(ev) : -1; }
     q.l2_ahead = (ahead >= 0) ? ahead : max_ctas;               // CTAs in flight = distance to the slot's next CTA
     kern<<<grid, NT, bytes, st>>>(q);
     return cudaGetLastError();

@@ -795,31 +795,35 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
     }
 }
 
+// Per-device launch configuration: the dynamic-shared-memory opt-in is a per-device function attribute and
+// the L2 prefetch distance depends on the device's SM count, so neither may be cached per process (a
+// context may live on any device, several devices may be driven by one process).
+constexpr int MAX_DEVICES = 64;
 template <int FORM, int STAGE, bool DIAG>
 cudaError_t launch_rb(const KParams &p, cudaStream_t st) {
     auto kern = (FORM == 0) ? substage_rb_kernel<STAGE, DIAG> : substage_rbd_kernel<STAGE, DIAG>;
     constexpr size_t bytes = (FORM == 0) ? SMEM_BYTES : SMEM_BYTES_D;
     constexpr int cells_x = (FORM == 0) ? TX : TXD;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    static int ahead[MAX_DEVICES] = {};                     // 0 = this device is not configured yet
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    if (ahead[dev] == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        int sms = 0, occ = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, bytes);
+        if (e != cudaSuccess) return e;
+        const char *env = getenv("SWMHD_L2_AHEAD");
+        const int a = env ? atoi(env) : (occ < 1 ? 1 : occ) * sms;   // CTAs in flight = distance to the slot's next tile
+        ahead[dev] = a < 1 ? 1 : a;
     }
     const int tiles_x = (p.Nx + cells_x - 1) / cells_x;
     const int tiles_y = (p.row_end - p.row_begin + TYB - 1) / TYB;
-    static int ahead = -1;
-    if (ahead < 0) {
-        int dev = 0, sms = 0, occ = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, bytes);
-        if (e != cudaSuccess) return e;
-        const char *env = getenv("SWMHD_L2_AHEAD");
-        ahead = env ? atoi(env) : (occ < 1 ? 1 : occ) * sms;   // CTAs in flight = distance to the slot's next tile
-    }
     KParams q = p;
-    q.l2_ahead = ahead;
+    q.l2_ahead = ahead[dev];
     kern<<<tiles_x * tiles_y, NT, bytes, st>>>(q);
     return cudaGetLastError();
 }

@@ -1,7 +1,16 @@
 // swmhd_api.cu — the C ABI of include/swmhd.h over the CUDA kernels.
-// Host-side orchestration only: buffers, streams, launch sequencing, clock.
+// Host-side orchestration only: buffers, streams, launch sequencing, the NCCL halo exchange, clock.
+//
+// A context drives one or more y-slabs:
+//   * one slab on one GPU (the default),
+//   * n_gpus slabs on n_gpus devices of THIS process (cfg.n_gpus > 1; ncclCommInitAll), or
+//   * one slab of a ring of `world` processes (cfg.world > 1; ncclCommInitRank in swmhd_comm_init).
+// Per substage and slab: the tile rows next to the slab edges on a high-priority stream, x wrap of
+// the rows to be sent, ncclSend/ncclRecv of 3 contiguous parent rows per field and direction (one
+// NCCL group per substage), the interior concurrently on the main stream, event join.
 #include "../../include/swmhd.h"
 #include "kparams.h"
+#include "nccl_dyn.h"
 
 #include <cmath>
 #include <cstdio>
@@ -13,31 +22,49 @@
 
 using namespace swmhd;
 
-struct swmhd_ctx {
-    swmhd_config cfg;
-    int Nx, Ny, P;              // local slab
-    int rows[4];
-    size_t len[4];
-    double *U[2][4];
+namespace {
+
+struct Slab {
+    int dev = 0, index = 0;     // CUDA ordinal; position in the y ring (0 = south)
+    int j0 = 0, Ny = 0;         // global row offset, rows owned
+    int rows[4] = {0, 0, 0, 0};
+    size_t len[4] = {0, 0, 0, 0};
+    double *U[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    double *G[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *O[4] = {nullptr, nullptr, nullptr, nullptr};   // staging of the asynchronous field writer (lazy)
     CUtensorMap tmap[2][4];     // TMA descriptors of U[b][k]: 2-D (P x rows) FP64, box (TX+6) x (TY+6)
     CUtensorMap tmap_rb[2][4];  // same arrays, box of the row-blocked kernel
+    double *d_partials = nullptr, *d_diag = nullptr, *d_stage = nullptr, *d_red = nullptr;
+    int nblocks_diag = 0, ntiles = 0;
+    cudaStream_t main = nullptr, edge = nullptr, copy = nullptr;
+    bool own_streams = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_edge = nullptr, ev_main = nullptr, ev_out_ready = nullptr, ev_out_done = nullptr;
+    int ntr = 0, n_south = 0, n_north = 0;   // tile rows (units of the 8-row launch granularity); edge groups
+    ncclComm_t comm = nullptr;
+    int pending_slot = -1;
+    bool out_in_flight = false;
+};
+
+} // namespace
+
+struct swmhd_ctx {
+    swmhd_config cfg;
+    int Nx, P;
+    int nslabs_total;           // slabs in the y ring (n_gpus or world)
+    std::vector<Slab> slabs;    // the slabs this process drives
     int use_tma, use_rb;
-    double *G[4];
-    int cur;                    // U[cur] = current state
-    double *d_partials, *d_diag, *d_stage; // diag partials; d_diag holds NDIAG doubles per slot
+    int tx, ty;                 // 8-row launch granularity of the tile rows
+    int edge_tr;                // tile rows per edge group (row-blocked kernel: one 16-row tile)
+    int cur;                    // U[cur] = current state (all slabs alike)
     int diag_slots;
-    int nblocks_diag, ntiles;
-    cudaStream_t main, edge;
-    bool own_streams;
-    cudaEvent_t ev0, ev1, ev_edge, ev_main;
+    bool comm_ready;            // NCCL communicators exist (or are not needed)
+    bool in_substage;
+    int last_stage;             // last completed stage of the step in flight (0: between steps)
+    double pending_dt;
+    int armed_slot;             // >= 0: the next stage-1 substage also produces diagnostics into this slot
     double time;
     int64_t iter, launches;
     double last_ms;
-    int tx, ty, ntr, n_last;    // tile geometry: tile rows, tile rows in the north edge group
-    bool in_substage;
-    double pending_dt;
-    int armed_slot;             // >= 0: the next stage-1 slab substage also produces diagnostics into this slot
-    int pending_slot;
     std::string err;
 };
 
@@ -80,6 +107,17 @@ static bool encode_field_map(CUtensorMap *tm, double *base, int P, int rows, int
         }                                                                                     \
     } while (0)
 
+#define NK(call)                                                                              \
+    do {                                                                                      \
+        ncclResult_t r_ = (call);                                                             \
+        if (r_ != ncclSuccess) {                                                              \
+            char buf_[512];                                                                   \
+            snprintf(buf_, sizeof buf_, "%s:%d: %s: %s", __FILE__, __LINE__, #call, nccl_api()->GetErrorString(r_)); \
+            ctx->err = buf_;                                                                  \
+            return SWMHD_ERR_NCCL;                                                            \
+        }                                                                                     \
+    } while (0)
+
 static int fail(swmhd_ctx *ctx, int code, const char *msg) {
     if (ctx) ctx->err = msg; else g_create_err = msg;
     return code;
@@ -89,6 +127,85 @@ extern "C" int swmhd_abi_version(void) { return SWMHD_ABI_VERSION; }
 
 extern "C" const char *swmhd_last_error(const swmhd_ctx *ctx) {
     return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int swmhd_split_rows(int Ny, int nslabs, int index, int *j0, int *ny) {
+    if (nslabs < 1 || index < 0 || index >= nslabs || Ny < nslabs || !j0 || !ny) return SWMHD_ERR_ARG;
+    const int base = Ny / nslabs, rem = Ny % nslabs;       // the first `rem` slabs take one row more
+    *j0 = index * base + (index < rem ? index : rem);
+    *ny = base + (index < rem ? 1 : 0);
+    return SWMHD_OK;
+}
+
+static bool multi(const swmhd_ctx *ctx) { return ctx->nslabs_total > 1; }
+
+// ---------------------------------------------------------------------------
+static int create_slab(swmhd_ctx *ctx, Slab &s, std::string &why) {
+    const swmhd_config &c = ctx->cfg;
+    cudaError_t e;
+    auto bad = [&](const char *what, cudaError_t er) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s (device %d): %s", what, s.dev, cudaGetErrorString(er));
+        why = buf;
+        return SWMHD_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(s.dev)) != cudaSuccess) return bad("cudaSetDevice", e);
+    for (int k = 0; k < 4; k++) {
+        s.rows[k] = s.Ny + 6 + ((k == SWMHD_V && c.topo_y == SWMHD_BOUNDED) ? 1 : 0);
+        s.len[k] = (size_t)ctx->P * s.rows[k];
+    }
+    s.ntr = (s.Ny + ctx->ty - 1) / ctx->ty;
+    // edge groups: whole tiles of the kernel that runs (one 16-row tile of the row-blocked kernel = two
+    // 8-row tile rows), the north group starts on a tile boundary and holds at least the 3 rows to be sent
+    const int et = ctx->edge_tr;
+    s.n_south = et;
+    int north0 = ((s.Ny - 3) / (et * ctx->ty)) * et;
+    if (north0 < 0) north0 = 0;
+    s.n_north = s.ntr - north0;
+    for (int k = 0; k < 4; k++) {
+        const size_t bytes = s.len[k] * sizeof(double);
+        for (int b = 0; b < 2; b++) {
+            if ((e = cudaMalloc(&s.U[b][k], bytes)) != cudaSuccess) return bad("cudaMalloc state", e);
+            if ((e = cudaMemset(s.U[b][k], 0, bytes)) != cudaSuccess) return bad("cudaMemset", e);
+        }
+        if ((e = cudaMalloc(&s.G[k], bytes)) != cudaSuccess) return bad("cudaMalloc tendency", e);
+        if ((e = cudaMemset(s.G[k], 0, bytes)) != cudaSuccess) return bad("cudaMemset", e);
+    }
+    for (int b = 0; b < 2 && ctx->use_tma; b++)
+        for (int k = 0; k < 4 && ctx->use_tma; k++)
+            if (!encode_field_map(&s.tmap[b][k], s.U[b][k], ctx->P, s.rows[k], ctx->tx + 6, ctx->ty + 6)) ctx->use_tma = 0;
+    if (!ctx->use_tma) ctx->use_rb = 0;
+    if (ctx->use_rb) {
+        int rtx, rty;
+        substage_rb_tile(&rtx, &rty);
+        for (int b = 0; b < 2 && ctx->use_rb; b++)
+            for (int k = 0; k < 4 && ctx->use_rb; k++)
+                if (!encode_field_map(&s.tmap_rb[b][k], s.U[b][k], ctx->P, s.rows[k], rtx + 6, rty + 6)) ctx->use_rb = 0;
+    }
+    // per-tile diagnostic partials: one slot per (8-row tile row, tile column) of the kernel that runs stage 1
+    const int diag_tiles_x = (ctx->use_rb && (substage_rb_stage_mask() & 1)) ? substage_rb_tiles_x(c.formulation, ctx->Nx)
+                                                                              : (ctx->Nx + ctx->tx - 1) / ctx->tx;
+    s.nblocks_diag = diag_blocks(ctx->Nx, s.Ny);
+    s.ntiles = diag_tiles_x * s.ntr;
+    if (s.ntiles > s.nblocks_diag) s.nblocks_diag = s.ntiles;   // d_partials serves both diag paths
+    if ((e = cudaMalloc(&s.d_partials, (size_t)s.nblocks_diag * NDIAG * sizeof(double))) != cudaSuccess) return bad("cudaMalloc diag", e);
+    if ((e = cudaMalloc(&s.d_diag, (size_t)ctx->diag_slots * NDIAG * sizeof(double))) != cudaSuccess) return bad("cudaMalloc diag", e);
+    if ((e = cudaMalloc(&s.d_stage, (size_t)diag_stage_doubles() * sizeof(double))) != cudaSuccess) return bad("cudaMalloc diag", e);
+    if ((e = cudaMemset(s.d_stage, 0, (size_t)diag_stage_doubles() * sizeof(double))) != cudaSuccess) return bad("cudaMemset", e);   // ticket word = 0
+    if ((e = cudaMalloc(&s.d_red, (size_t)2 * ctx->diag_slots * NDIAG * sizeof(double))) != cudaSuccess) return bad("cudaMalloc diag", e);
+    int lo, hi;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&s.main, cudaStreamNonBlocking, lo)) != cudaSuccess) return bad("stream", e);
+    if ((e = cudaStreamCreateWithPriority(&s.edge, cudaStreamNonBlocking, hi)) != cudaSuccess) return bad("stream", e);
+    if ((e = cudaStreamCreateWithPriority(&s.copy, cudaStreamNonBlocking, lo)) != cudaSuccess) return bad("stream", e);
+    s.own_streams = true;
+    if ((e = cudaEventCreate(&s.ev0)) != cudaSuccess) return bad("event", e);
+    if ((e = cudaEventCreate(&s.ev1)) != cudaSuccess) return bad("event", e);
+    if ((e = cudaEventCreateWithFlags(&s.ev_edge, cudaEventDisableTiming)) != cudaSuccess) return bad("event", e);
+    if ((e = cudaEventCreateWithFlags(&s.ev_main, cudaEventDisableTiming)) != cudaSuccess) return bad("event", e);
+    if ((e = cudaEventCreateWithFlags(&s.ev_out_ready, cudaEventDisableTiming)) != cudaSuccess) return bad("event", e);
+    if ((e = cudaEventCreateWithFlags(&s.ev_out_done, cudaEventDisableTiming)) != cudaSuccess) return bad("event", e);
+    return SWMHD_OK;
 }
 
 extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
@@ -106,6 +223,10 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
     if (c->world < 1 || c->rank < 0 || c->rank >= c->world) return fail(nullptr, SWMHD_ERR_ARG, "bad rank/world");
     if (c->slab_ny < 8 || c->slab_j0 < 0 || c->slab_j0 + c->slab_ny > c->Ny) return fail(nullptr, SWMHD_ERR_ARG, "bad slab (need >= 8 rows)");
     if (c->world == 1 && (c->slab_j0 != 0 || c->slab_ny != c->Ny)) return fail(nullptr, SWMHD_ERR_ARG, "world == 1 needs the full domain");
+    const int ngpu = c->n_gpus > 1 ? c->n_gpus : 1;
+    if (c->n_gpus < 0 || ngpu > SWMHD_MAX_GPUS) return fail(nullptr, SWMHD_ERR_ARG, "n_gpus must be in 0..8");
+    if (ngpu > 1 && c->world != 1) return fail(nullptr, SWMHD_ERR_ARG, "n_gpus > 1 (single process) and world > 1 (one process per GPU) are exclusive");
+    if (ngpu > 1 && c->Ny / ngpu < 8) return fail(nullptr, SWMHD_ERR_ARG, "n_gpus > 1 needs at least 8 rows per slab");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -113,169 +234,267 @@ extern "C" int swmhd_create(const swmhd_config *c, swmhd_ctx **out) {
         cudaGetLastError();
         return fail(nullptr, SWMHD_ERR_NODEVICE, "no CUDA device: libswmhd_cuda has no CPU fallback");
     }
-    if (c->device < 0 || c->device >= ndev) return fail(nullptr, SWMHD_ERR_ARG, "bad device ordinal");
+    if (ngpu == 1 && (c->device < 0 || c->device >= ndev)) return fail(nullptr, SWMHD_ERR_ARG, "bad device ordinal");
+    for (int d = 0; d < ngpu && ngpu > 1; d++) {
+        if (c->device_ids[d] < 0 || c->device_ids[d] >= ndev) return fail(nullptr, SWMHD_ERR_ARG, "bad device_ids entry");
+        for (int d2 = 0; d2 < d; d2++)
+            if (c->device_ids[d2] == c->device_ids[d]) return fail(nullptr, SWMHD_ERR_ARG, "device_ids must be distinct");
+    }
 
     swmhd_ctx *ctx = new (std::nothrow) swmhd_ctx();
     if (!ctx) return fail(nullptr, SWMHD_ERR_ARG, "out of host memory");
     ctx->cfg = *c;
-    ctx->Nx = c->Nx; ctx->Ny = c->slab_ny; ctx->P = c->Nx + 6;
-    for (int k = 0; k < 4; k++) {
-        ctx->rows[k] = ctx->Ny + 6 + ((k == SWMHD_V && c->topo_y == SWMHD_BOUNDED) ? 1 : 0);
-        ctx->len[k] = (size_t)ctx->P * ctx->rows[k];
-        ctx->U[0][k] = ctx->U[1][k] = ctx->G[k] = nullptr;
-    }
-    ctx->cur = 0; ctx->time = 0; ctx->iter = 0; ctx->launches = 0; ctx->last_ms = 0; ctx->in_substage = false; ctx->armed_slot = -1; ctx->pending_slot = -1;
-    ctx->d_partials = ctx->d_diag = ctx->d_stage = nullptr; ctx->main = ctx->edge = nullptr; ctx->own_streams = false;
-    ctx->ev0 = ctx->ev1 = ctx->ev_edge = ctx->ev_main = nullptr;
+    ctx->Nx = c->Nx; ctx->P = c->Nx + 6;
+    ctx->nslabs_total = ngpu > 1 ? ngpu : c->world;
+    ctx->cur = 0; ctx->time = 0; ctx->iter = 0; ctx->launches = 0; ctx->last_ms = 0;
+    ctx->in_substage = false; ctx->last_stage = 0; ctx->pending_dt = 0; ctx->armed_slot = -1;
+    ctx->diag_slots = 1024;
+    ctx->comm_ready = (ctx->nslabs_total == 1);
     substage_tile(&ctx->tx, &ctx->ty);
-    ctx->ntr = (ctx->Ny + ctx->ty - 1) / ctx->ty;
-    ctx->n_last = (ctx->Ny - (ctx->ntr - 1) * ctx->ty >= 3) ? 1 : 2;
-
-    auto bail = [&](const char *what, cudaError_t er) {
-        char buf[256];
-        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(er));
-        g_create_err = buf;
-        swmhd_destroy(ctx);
-        return SWMHD_ERR_CUDA;
-    };
-    if ((e = cudaSetDevice(c->device)) != cudaSuccess) return bail("cudaSetDevice", e);
-    for (int k = 0; k < 4; k++) {
-        size_t bytes = ctx->len[k] * sizeof(double);
-        for (int b = 0; b < 2; b++) {
-            if ((e = cudaMalloc(&ctx->U[b][k], bytes)) != cudaSuccess) return bail("cudaMalloc state", e);
-            if ((e = cudaMemset(ctx->U[b][k], 0, bytes)) != cudaSuccess) return bail("cudaMemset", e);
-        }
-        if ((e = cudaMalloc(&ctx->G[k], bytes)) != cudaSuccess) return bail("cudaMalloc tendency", e);
-        if ((e = cudaMemset(ctx->G[k], 0, bytes)) != cudaSuccess) return bail("cudaMemset", e);
-    }
     // TMA tile loads need a 16-byte row pitch (even Nx); otherwise the kernels use plain loads
     ctx->use_tma = (ctx->P % 2 == 0) ? 1 : 0;
-    for (int b = 0; b < 2 && ctx->use_tma; b++)
-        for (int k = 0; k < 4 && ctx->use_tma; k++)
-            if (!encode_field_map(&ctx->tmap[b][k], ctx->U[b][k], ctx->P, ctx->rows[k], ctx->tx + 6, ctx->ty + 6)) ctx->use_tma = 0;
     if (getenv("SWMHD_NO_TMA")) ctx->use_tma = 0;
     // row-blocked kernels (FAST arithmetic): taller box; their 8-row launch granularity is ctx->ty
     ctx->use_rb = (ctx->use_tma && ctx->ty == 8 && c->arith == SWMHD_ARITH_FAST) ? 1 : 0;
-    if (ctx->use_rb) {
-        int rtx, rty;
-        substage_rb_tile(&rtx, &rty);
-        for (int b = 0; b < 2 && ctx->use_rb; b++)
-            for (int k = 0; k < 4 && ctx->use_rb; k++)
-                if (!encode_field_map(&ctx->tmap_rb[b][k], ctx->U[b][k], ctx->P, ctx->rows[k], rtx + 6, rty + 6)) ctx->use_rb = 0;
-    }
     if (getenv("SWMHD_NO_RB")) ctx->use_rb = 0;
-    // per-tile diagnostic partials: one slot per (8-row tile row, tile column) of the kernel that runs stage 1
-    const int diag_tiles_x = (ctx->use_rb && (substage_rb_stage_mask() & 1)) ? substage_rb_tiles_x(c->formulation, ctx->Nx)
-                                                                             : (ctx->Nx + ctx->tx - 1) / ctx->tx;
-    ctx->nblocks_diag = diag_blocks(ctx->Nx, ctx->Ny);
-    ctx->ntiles = diag_tiles_x * ctx->ntr;
-    if (ctx->ntiles > ctx->nblocks_diag) ctx->nblocks_diag = ctx->ntiles;   // d_partials serves both diag paths
-    ctx->diag_slots = 1024;
-    if ((e = cudaMalloc(&ctx->d_partials, (size_t)ctx->nblocks_diag * NDIAG * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
-    if ((e = cudaMalloc(&ctx->d_diag, (size_t)ctx->diag_slots * NDIAG * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
-    if ((e = cudaMalloc(&ctx->d_stage, (size_t)diag_stage_doubles() * sizeof(double))) != cudaSuccess) return bail("cudaMalloc diag", e);
-    int lo, hi;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if ((e = cudaStreamCreateWithPriority(&ctx->main, cudaStreamNonBlocking, lo)) != cudaSuccess) return bail("stream", e);
-    if ((e = cudaStreamCreateWithPriority(&ctx->edge, cudaStreamNonBlocking, hi)) != cudaSuccess) return bail("stream", e);
-    ctx->own_streams = true;
-    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return bail("event", e);
-    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return bail("event", e);
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_edge, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
-    if ((e = cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming)) != cudaSuccess) return bail("event", e);
+    {
+        int rtx = 0, rty = 8;
+        if (ctx->use_rb) substage_rb_tile(&rtx, &rty);
+        ctx->edge_tr = (ctx->use_rb && substage_rb_stage_mask() == 7) ? rty / ctx->ty : 1;
+        if (ctx->edge_tr < 1) ctx->edge_tr = 1;
+    }
+    ctx->slabs.resize(ngpu);
+    for (int d = 0; d < ngpu; d++) {
+        Slab &s = ctx->slabs[d];
+        if (ngpu > 1) {
+            s.dev = c->device_ids[d]; s.index = d;
+            swmhd_split_rows(c->Ny, ngpu, d, &s.j0, &s.Ny);
+        } else {
+            s.dev = c->device; s.index = c->rank; s.j0 = c->slab_j0; s.Ny = c->slab_ny;
+        }
+    }
+    for (auto &s : ctx->slabs) {
+        std::string why;
+        int rc = create_slab(ctx, s, why);
+        if (rc != SWMHD_OK) {
+            g_create_err = why;
+            swmhd_destroy(ctx);
+            return rc;
+        }
+    }
+    if (ngpu > 1) {     // one communicator per device of this process
+        const NcclApi *api = nccl_api();
+        if (!api) { g_create_err = std::string("n_gpus > 1 needs NCCL: ") + nccl_load_error(); swmhd_destroy(ctx); return SWMHD_ERR_NCCL; }
+        std::vector<ncclComm_t> comms(ngpu);
+        std::vector<int> devs(ngpu);
+        for (int d = 0; d < ngpu; d++) devs[d] = ctx->slabs[d].dev;
+        ncclResult_t r = api->CommInitAll(comms.data(), ngpu, devs.data());
+        if (r != ncclSuccess) { g_create_err = std::string("ncclCommInitAll: ") + api->GetErrorString(r); swmhd_destroy(ctx); return SWMHD_ERR_NCCL; }
+        for (int d = 0; d < ngpu; d++) ctx->slabs[d].comm = comms[d];
+        ctx->comm_ready = true;
+    }
     *out = ctx;
     return SWMHD_OK;
 }
 
 extern "C" void swmhd_destroy(swmhd_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->cfg.device);
-    cudaDeviceSynchronize();
-    for (int k = 0; k < 4; k++) {
-        cudaFree(ctx->U[0][k]); cudaFree(ctx->U[1][k]); cudaFree(ctx->G[k]);
+    for (auto &s : ctx->slabs) {
+        cudaSetDevice(s.dev);
+        cudaDeviceSynchronize();
+        if (s.comm && nccl_api()) nccl_api()->CommDestroy(s.comm);
+        for (int k = 0; k < 4; k++) {
+            cudaFree(s.U[0][k]); cudaFree(s.U[1][k]); cudaFree(s.G[k]); cudaFree(s.O[k]);
+        }
+        cudaFree(s.d_partials); cudaFree(s.d_diag); cudaFree(s.d_stage); cudaFree(s.d_red);
+        if (s.own_streams) {
+            if (s.main) cudaStreamDestroy(s.main);
+            if (s.edge) cudaStreamDestroy(s.edge);
+        }
+        if (s.copy) cudaStreamDestroy(s.copy);
+        for (cudaEvent_t ev : {s.ev0, s.ev1, s.ev_edge, s.ev_main, s.ev_out_ready, s.ev_out_done})
+            if (ev) cudaEventDestroy(ev);
+        cudaGetLastError();
     }
-    cudaFree(ctx->d_partials); cudaFree(ctx->d_diag); cudaFree(ctx->d_stage);
-    if (ctx->own_streams) {
-        if (ctx->main) cudaStreamDestroy(ctx->main);
-        if (ctx->edge) cudaStreamDestroy(ctx->edge);
-    }
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-    if (ctx->ev_edge) cudaEventDestroy(ctx->ev_edge);
-    if (ctx->ev_main) cudaEventDestroy(ctx->ev_main);
-    cudaGetLastError();
     delete ctx;
+}
+
+// ---- NCCL ------------------------------------------------------------------------------------
+extern "C" int swmhd_comm_unique_id(void *id, size_t nbytes) {
+    if (!id || nbytes < SWMHD_COMM_ID_BYTES) return fail(nullptr, SWMHD_ERR_ARG, "id buffer must hold SWMHD_COMM_ID_BYTES");
+    const NcclApi *api = nccl_api();
+    if (!api) { g_create_err = std::string("NCCL not available: ") + nccl_load_error(); return SWMHD_ERR_NCCL; }
+    static_assert(sizeof(ncclUniqueId) == SWMHD_COMM_ID_BYTES, "unique id size");
+    ncclUniqueId uid;
+    ncclResult_t r = api->GetUniqueId(&uid);
+    if (r != ncclSuccess) { g_create_err = std::string("ncclGetUniqueId: ") + api->GetErrorString(r); return SWMHD_ERR_NCCL; }
+    memcpy(id, &uid, sizeof uid);
+    return SWMHD_OK;
+}
+
+extern "C" int swmhd_comm_init(swmhd_ctx *ctx, const void *id, size_t nbytes) {
+    if (!ctx) return SWMHD_ERR_ARG;
+    if (!id || nbytes < SWMHD_COMM_ID_BYTES) return fail(ctx, SWMHD_ERR_ARG, "id buffer must hold SWMHD_COMM_ID_BYTES");
+    if (ctx->cfg.world < 2) return fail(ctx, SWMHD_ERR_STATE, "swmhd_comm_init is for world > 1 contexts");
+    if (ctx->comm_ready) return fail(ctx, SWMHD_ERR_STATE, "communicator already initialised");
+    const NcclApi *api = nccl_api();
+    if (!api) { ctx->err = std::string("NCCL not available: ") + nccl_load_error(); return SWMHD_ERR_NCCL; }
+    Slab &s = ctx->slabs[0];
+    CK(cudaSetDevice(s.dev));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    NK(api->CommInitRank(&s.comm, ctx->cfg.world, uid, ctx->cfg.rank));
+    ctx->comm_ready = true;
+    return SWMHD_OK;
+}
+
+// neighbours of slab `index` in the y ring: -1 at a wall
+static void ring_neighbours(const swmhd_ctx *ctx, int index, int *south, int *north) {
+    const int n = ctx->nslabs_total;
+    const bool per = (ctx->cfg.topo_y == SWMHD_PERIODIC);
+    *south = index > 0 ? index - 1 : (per ? n - 1 : -1);
+    *north = index < n - 1 ? index + 1 : (per ? 0 : -1);
+}
+
+// One halo exchange of `nf` fields: base[slab][k] are parent arrays laid out like the state.  My north
+// edge rows go to the north neighbour's south halo and vice versa; sends and receives towards one peer
+// are issued in matching order (north rows first), which also covers a ring of two.
+static int exchange(swmhd_ctx *ctx, double *(*base)[4], int nf, bool on_edge_stream) {
+    if (!multi(ctx)) return SWMHD_OK;
+    const NcclApi *api = nccl_api();
+    const size_t n = (size_t)3 * ctx->P;
+    NK(api->GroupStart());
+    for (size_t si = 0; si < ctx->slabs.size(); si++) {
+        Slab &s = ctx->slabs[si];
+        int so, no;
+        ring_neighbours(ctx, s.index, &so, &no);
+        cudaStream_t st = on_edge_stream ? s.edge : s.main;
+        for (int k = 0; k < nf; k++) {
+            double *a = base[si][k];
+            double *north_send = a + (size_t)s.Ny * ctx->P, *south_send = a + (size_t)3 * ctx->P;
+            double *south_halo = a, *north_halo = a + (size_t)(s.Ny + 3) * ctx->P;
+            if (no >= 0) NK(api->Send(north_send, n, ncclFloat64, no, s.comm, st));
+            if (so >= 0) NK(api->Recv(south_halo, n, ncclFloat64, so, s.comm, st));
+            if (so >= 0) NK(api->Send(south_send, n, ncclFloat64, so, s.comm, st));
+            if (no >= 0) NK(api->Recv(north_halo, n, ncclFloat64, no, s.comm, st));
+        }
+    }
+    NK(api->GroupEnd());
+    return SWMHD_OK;
+}
+
+static int exchange_state(swmhd_ctx *ctx, int buf, bool on_edge_stream) {
+    double *base[SWMHD_MAX_GPUS][4];
+    for (size_t si = 0; si < ctx->slabs.size(); si++)
+        for (int k = 0; k < 4; k++) base[si][k] = ctx->slabs[si].U[buf][k];
+    return exchange(ctx, base, 4, on_edge_stream);
+}
+
+static int need_comm(swmhd_ctx *ctx) {
+    if (multi(ctx) && !ctx->comm_ready)
+        return fail(ctx, SWMHD_ERR_STATE, "world > 1: call swmhd_comm_init first (or drive the exchange with substage_edges/interior/finish)");
+    return SWMHD_OK;
+}
+
+// ---- fields -------------------------------------------------------------------------------------
+static bool in_process_multi(const swmhd_ctx *ctx) { return ctx->slabs.size() > 1; }
+
+static size_t host_len(const swmhd_ctx *ctx, int field) {
+    if (!in_process_multi(ctx)) return ctx->slabs[0].len[field];
+    const int rows = ctx->cfg.Ny + 6 + ((field == SWMHD_V && ctx->cfg.topo_y == SWMHD_BOUNDED) ? 1 : 0);
+    return (size_t)ctx->P * rows;
 }
 
 extern "C" size_t swmhd_field_len(const swmhd_ctx *ctx, int field) {
     if (!ctx || field < 0 || field > 3) return 0;
-    return ctx->len[field];
+    return host_len(ctx, field);
 }
 
 extern "C" int swmhd_set_field(swmhd_ctx *ctx, int field, const double *host, size_t n) {
     if (!ctx) return SWMHD_ERR_ARG;
     if (field < 0 || field > 3 || !host) return fail(ctx, SWMHD_ERR_ARG, "bad field/host");
-    if (n != ctx->len[field]) return fail(ctx, SWMHD_ERR_ARG, "host buffer is not the parent array of this field (length mismatch)");
-    CK(cudaSetDevice(ctx->cfg.device));
-    CK(cudaMemcpyAsync(ctx->U[ctx->cur][field], host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->main));
-    CK(cudaStreamSynchronize(ctx->main));
+    if (n != host_len(ctx, field)) return fail(ctx, SWMHD_ERR_ARG, "host buffer is not the parent array of this field (length mismatch)");
+    // every slab takes its rows with their 3 halo rows on each side out of the (global) parent array
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        const size_t off = in_process_multi(ctx) ? (size_t)s.j0 * ctx->P : 0;
+        CK(cudaMemcpyAsync(s.U[ctx->cur][field], host + off, s.len[field] * sizeof(double), cudaMemcpyHostToDevice, s.main));
+    }
+    for (auto &s : ctx->slabs) { CK(cudaSetDevice(s.dev)); CK(cudaStreamSynchronize(s.main)); }
     return SWMHD_OK;
+}
+
+// rows [lo, hi) of slab s that it contributes to a gathered parent array: its interior rows, the end slabs
+// also the global halo rows (and the wall row of v|vh)
+static void gather_rows(const swmhd_ctx *ctx, const Slab &s, int field, int *lo, int *hi) {
+    *lo = (s.index == 0) ? 0 : 3;
+    *hi = (s.index == ctx->nslabs_total - 1) ? s.rows[field] : 3 + s.Ny;
 }
 
 extern "C" int swmhd_get_field(swmhd_ctx *ctx, int field, double *host, size_t n) {
     if (!ctx) return SWMHD_ERR_ARG;
     if (field < 0 || field > 3 || !host) return fail(ctx, SWMHD_ERR_ARG, "bad field/host");
-    if (n != ctx->len[field]) return fail(ctx, SWMHD_ERR_ARG, "host buffer is not the parent array of this field (length mismatch)");
-    CK(cudaSetDevice(ctx->cfg.device));
-    CK(cudaMemcpyAsync(host, ctx->U[ctx->cur][field], n * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
-    CK(cudaStreamSynchronize(ctx->main));
+    if (n != host_len(ctx, field)) return fail(ctx, SWMHD_ERR_ARG, "host buffer is not the parent array of this field (length mismatch)");
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        if (!in_process_multi(ctx)) {
+            CK(cudaMemcpyAsync(host, s.U[ctx->cur][field], n * sizeof(double), cudaMemcpyDeviceToHost, s.main));
+        } else {
+            int lo, hi;
+            gather_rows(ctx, s, field, &lo, &hi);
+            CK(cudaMemcpyAsync(host + (size_t)(s.j0 + lo) * ctx->P, s.U[ctx->cur][field] + (size_t)lo * ctx->P,
+                               (size_t)(hi - lo) * ctx->P * sizeof(double), cudaMemcpyDeviceToHost, s.main));
+        }
+    }
+    for (auto &s : ctx->slabs) { CK(cudaSetDevice(s.dev)); CK(cudaStreamSynchronize(s.main)); }
     return SWMHD_OK;
 }
 
 // ---------------------------------------------------------------------------
-static HaloParams halo_params(swmhd_ctx *ctx, double *const U[4], int j_lo, int j_hi, bool y_part) {
+static HaloParams halo_params(swmhd_ctx *ctx, const Slab &s, double *const U[4], int j_lo, int j_hi, bool y_part) {
     const swmhd_config &c = ctx->cfg;
     HaloParams h;
-    h.Nx = ctx->Nx; h.Ny = ctx->Ny; h.P = ctx->P;
+    h.Nx = ctx->Nx; h.Ny = s.Ny; h.P = ctx->P;
     h.by = (c.topo_y == SWMHD_BOUNDED);
-    h.first = (c.rank == 0); h.last = (c.rank == c.world - 1);
+    h.first = (s.index == 0); h.last = (s.index == ctx->nslabs_total - 1);
     h.y_mode = 0;
     if (y_part) {
         if (h.by) h.y_mode = 2;
-        else if (c.world == 1) h.y_mode = 1;
+        else if (!multi(ctx)) h.y_mode = 1;
     }
     h.grad = c.A_gradient_bc; h.gs = c.A_grad_south; h.gn = c.A_grad_north; h.dy = c.dy;
     h.j_lo = j_lo; h.j_hi = j_hi;
-    for (int k = 0; k < 4; k++) { h.U[k] = U[k]; h.rows[k] = ctx->rows[k]; }
+    for (int k = 0; k < 4; k++) { h.U[k] = U[k]; h.rows[k] = s.rows[k]; }
     return h;
 }
 
-static KParams kparams(swmhd_ctx *ctx, double dt, int stage) {
+static KParams kparams(swmhd_ctx *ctx, const Slab &s, double dt, int stage) {
     const swmhd_config &c = ctx->cfg;
     KParams p;
-    p.Nx = ctx->Nx; p.Ny = ctx->Ny; p.P = ctx->P;
-    p.gj0 = c.slab_j0; p.NyG = c.Ny; p.by = (c.topo_y == SWMHD_BOUNDED);
-    p.tile_row0 = 0; p.tile_rows = ctx->ntr;
-    for (int k = 0; k < 4; k++) p.rows[k] = ctx->rows[k];
+    p.Nx = ctx->Nx; p.Ny = s.Ny; p.P = ctx->P;
+    p.gj0 = s.j0; p.NyG = c.Ny; p.by = (c.topo_y == SWMHD_BOUNDED);
+    p.tile_row0 = 0; p.tile_rows = s.ntr;
+    for (int k = 0; k < 4; k++) p.rows[k] = s.rows[k];
     p.dx = c.dx; p.dy = c.dy; p.rdx = 1.0 / c.dx; p.rdy = 1.0 / c.dy; p.inv_az = 1.0 / (c.dx * c.dy);
     p.g = c.g; p.f = c.f; p.eps = c.weno_eps; p.h_ref = c.h_ref;
     p.dt = dt;
     p.gam = stage >= 1 ? RK_GAMMA[stage - 1] : 0.0;
     p.zet = stage >= 1 ? RK_ZETA[stage - 1] : 0.0;
     p.dtgam = dt * p.gam;
+    p.dtzet = dt * p.zet;
     for (int k = 0; k < 4; k++) {
-        p.Uo[k] = ctx->U[ctx->cur][k];
-        p.Un[k] = ctx->U[1 - ctx->cur][k];
-        p.G[k] = ctx->G[k];
+        p.Uo[k] = s.U[ctx->cur][k];
+        p.Un[k] = s.U[1 - ctx->cur][k];
+        p.G[k] = s.G[k];
     }
     p.diag = nullptr;
     p.use_tma = ctx->use_tma;
     if (ctx->use_tma)
-        for (int k = 0; k < 4; k++) p.tm[k] = ctx->tmap[ctx->cur][k];
+        for (int k = 0; k < 4; k++) p.tm[k] = s.tmap[ctx->cur][k];
     p.use_rb = ctx->use_rb;
     p.row_begin = p.row_end = 0;
     if (ctx->use_rb)
-        for (int k = 0; k < 4; k++) p.tm_rb[k] = ctx->tmap_rb[ctx->cur][k];
+        for (int k = 0; k < 4; k++) p.tm_rb[k] = s.tmap_rb[ctx->cur][k];
     return p;
 }
 
@@ -290,32 +509,123 @@ static void tick(swmhd_ctx *ctx, double dt, int stage) {
     double sdt = (stage == 1) ? RK_GAMMA[0] * dt : (RK_GAMMA[stage - 1] + RK_ZETA[stage - 1]) * dt;
     ctx->time += sdt;
     if (stage == 3) ctx->iter += 1;
+    ctx->last_stage = stage % 3;
+}
+
+static int sync_all(swmhd_ctx *ctx) {
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaStreamSynchronize(s.edge));
+        CK(cudaStreamSynchronize(s.main));
+    }
+    return SWMHD_OK;
 }
 
 extern "C" int swmhd_fill_halos(swmhd_ctx *ctx) {
     if (!ctx) return SWMHD_ERR_ARG;
-    CK(cudaSetDevice(ctx->cfg.device));
-    HaloParams h = halo_params(ctx, ctx->U[ctx->cur], 3, ctx->Ny + 2, true);
-    ctx->launches++;
-    CK(launch_halo(h, ctx->main));
-    CK(cudaStreamSynchronize(ctx->main));
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        HaloParams h = halo_params(ctx, s, s.U[ctx->cur], 3, s.Ny + 2, true);
+        ctx->launches++;
+        CK(launch_halo(h, s.main));
+    }
+    if (multi(ctx) && ctx->comm_ready) {      // y halos from the neighbours (x-wrapped rows travel, so corners are right)
+        int rc = exchange_state(ctx, ctx->cur, false);
+        if (rc) return rc;
+    }
+    return sync_all(ctx);
+}
+
+// ---- one substage of a slab: edges, interior ---------------------------------------------------------
+static int slab_edges(swmhd_ctx *ctx, Slab &s, double dt, int stage, cudaEvent_t e0) {
+    CK(cudaSetDevice(s.dev));
+    // the edge stream may not overwrite rows the previous substage's kernels still read
+    CK(cudaEventRecord(s.ev_main, s.main));
+    CK(cudaStreamWaitEvent(s.edge, s.ev_main, 0));
+    if (e0) CK(cudaEventRecord(e0, s.edge));
+    KParams p = kparams(ctx, s, dt, stage);
+    s.pending_slot = -1;
+    if (stage == 1 && ctx->armed_slot >= 0) {
+        p.diag = s.d_partials;
+        s.pending_slot = ctx->armed_slot;
+    }
+    const int ntr = s.ntr, ns = s.n_south, nn = s.n_north, ty = ctx->ty;
+    double *const *Un = s.U[1 - ctx->cur];
+    if (ntr <= ns + nn) {            // slab too thin to split: everything is "edge"
+        CK(launch_substage(ctx, p, stage, s.edge));
+        HaloParams h = halo_params(ctx, s, Un, 3, s.Ny + 2, true);
+        ctx->launches++;
+        CK(launch_halo(h, s.edge));
+    } else {
+        p.tile_row0 = 0; p.tile_rows = ns;
+        CK(launch_substage(ctx, p, stage, s.edge));
+        p.tile_row0 = ntr - nn; p.tile_rows = nn;
+        CK(launch_substage(ctx, p, stage, s.edge));
+        // x wrap of the rows that are about to be sent, and wall BCs on end slabs
+        HaloParams h = halo_params(ctx, s, Un, 3, 3 + ns * ty - 1, true);
+        ctx->launches++;
+        CK(launch_halo(h, s.edge));
+        HaloParams h2 = halo_params(ctx, s, Un, 3 + (ntr - nn) * ty, s.Ny + 2, false);
+        ctx->launches++;
+        CK(launch_halo(h2, s.edge));
+    }
     return SWMHD_OK;
 }
 
-// one substage on the main stream, no host synchronisation
-static int substage_async(swmhd_ctx *ctx, double dt, int stage, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr, int diag_slot = -1) {
-    KParams p = kparams(ctx, dt, stage);
-    if (diag_slot >= 0 && stage == 1) p.diag = ctx->d_partials;
-    if (e0) CK(cudaEventRecord(e0, ctx->main));
-    CK(launch_substage(ctx, p, stage, ctx->main));
-    if (e1) CK(cudaEventRecord(e1, ctx->main));
-    if (diag_slot >= 0 && stage == 1) {
+static int slab_interior(swmhd_ctx *ctx, Slab &s, double dt, int stage) {
+    CK(cudaSetDevice(s.dev));
+    const int ntr = s.ntr, ns = s.n_south, nn = s.n_north;
+    if (ntr > ns + nn) {
+        KParams p = kparams(ctx, s, dt, stage);
+        if (stage == 1 && s.pending_slot >= 0) p.diag = s.d_partials;
+        p.tile_row0 = ns; p.tile_rows = ntr - nn - ns;
+        CK(launch_substage(ctx, p, stage, s.main));
+        HaloParams h = halo_params(ctx, s, s.U[1 - ctx->cur], 3 + ns * ctx->ty, 3 + (ntr - nn) * ctx->ty - 1, false);
         ctx->launches++;
-        CK(launch_diag_final(ctx->d_partials, ctx->ntiles, ctx->d_stage, ctx->d_diag + (size_t)diag_slot * NDIAG, ctx->main));
+        CK(launch_halo(h, s.main));
     }
-    HaloParams h = halo_params(ctx, ctx->U[1 - ctx->cur], 3, ctx->Ny + 2, true);
-    ctx->launches++;
-    CK(launch_halo(h, ctx->main));
+    return SWMHD_OK;
+}
+
+static int slab_join(swmhd_ctx *ctx, Slab &s, cudaEvent_t e1) {
+    CK(cudaSetDevice(s.dev));
+    CK(cudaEventRecord(s.ev_edge, s.edge));
+    CK(cudaStreamWaitEvent(s.main, s.ev_edge, 0));
+    if (s.pending_slot >= 0) {       // fold the per-tile partials of edges + interior (fixed order)
+        ctx->launches++;
+        CK(launch_diag_final(s.d_partials, s.ntiles, s.d_stage, s.d_diag + (size_t)s.pending_slot * NDIAG, s.main));
+        s.pending_slot = -1;
+    }
+    if (e1) CK(cudaEventRecord(e1, s.main));
+    return SWMHD_OK;
+}
+
+// one substage of every local slab, no host synchronisation.  Single slab: one launch on the main stream.
+// Optional event pair around the fused substage kernel of slab 0 (single slab only).
+static int substage_async(swmhd_ctx *ctx, double dt, int stage, cudaEvent_t e0 = nullptr, cudaEvent_t e1 = nullptr, int diag_slot = -1) {
+    if (!multi(ctx)) {
+        Slab &s = ctx->slabs[0];
+        KParams p = kparams(ctx, s, dt, stage);
+        if (diag_slot >= 0 && stage == 1) p.diag = s.d_partials;
+        if (e0) CK(cudaEventRecord(e0, s.main));
+        CK(launch_substage(ctx, p, stage, s.main));
+        if (e1) CK(cudaEventRecord(e1, s.main));
+        if (diag_slot >= 0 && stage == 1) {
+            ctx->launches++;
+            CK(launch_diag_final(s.d_partials, s.ntiles, s.d_stage, s.d_diag + (size_t)diag_slot * NDIAG, s.main));
+        }
+        HaloParams h = halo_params(ctx, s, s.U[1 - ctx->cur], 3, s.Ny + 2, true);
+        ctx->launches++;
+        CK(launch_halo(h, s.main));
+    } else {
+        ctx->armed_slot = (stage == 1) ? diag_slot : -1;
+        for (auto &s : ctx->slabs) { int rc = slab_edges(ctx, s, dt, stage, nullptr); if (rc) return rc; }
+        ctx->armed_slot = -1;
+        int rc = exchange_state(ctx, 1 - ctx->cur, true);
+        if (rc) return rc;
+        for (auto &s : ctx->slabs) { rc = slab_interior(ctx, s, dt, stage); if (rc) return rc; }
+        for (auto &s : ctx->slabs) { rc = slab_join(ctx, s, nullptr); if (rc) return rc; }
+    }
     ctx->cur = 1 - ctx->cur;
     tick(ctx, dt, stage);
     return SWMHD_OK;
@@ -324,26 +634,16 @@ static int substage_async(swmhd_ctx *ctx, double dt, int stage, cudaEvent_t e0 =
 extern "C" int swmhd_substage(swmhd_ctx *ctx, double dt, int stage) {
     if (!ctx) return SWMHD_ERR_ARG;
     if (stage < 1 || stage > 3) return fail(ctx, SWMHD_ERR_ARG, "stage must be 1, 2 or 3");
-    if (ctx->cfg.world != 1) return fail(ctx, SWMHD_ERR_STATE, "swmhd_substage is single-slab; use substage_edges/interior/finish");
-    CK(cudaSetDevice(ctx->cfg.device));
-    int rc = substage_async(ctx, dt, stage);
+    if (ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "a host-driven substage is in flight");
+    int rc = need_comm(ctx);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->main));
-    return SWMHD_OK;
+    CK(cudaSetDevice(ctx->slabs[0].dev));
+    rc = substage_async(ctx, dt, stage);
+    if (rc) return rc;
+    return sync_all(ctx);
 }
 
-static int diag_async(swmhd_ctx *ctx, int slot) {
-    const swmhd_config &c = ctx->cfg;
-    DiagParams d;
-    d.Nx = ctx->Nx; d.Ny = ctx->Ny; d.P = ctx->P; d.form = c.formulation;
-    d.dx = c.dx; d.dy = c.dy; d.g = c.g; d.h_ref = c.h_ref;
-    for (int k = 0; k < 4; k++) d.U[k] = ctx->U[ctx->cur][k];
-    d.partials = ctx->d_partials; d.nblocks = diag_blocks(ctx->Nx, ctx->Ny); d.stage = ctx->d_stage;
-    ctx->launches += 2;
-    CK(launch_diag(d, ctx->d_diag + (size_t)slot * NDIAG, ctx->main));
-    return SWMHD_OK;
-}
-
+// ---- diagnostics --------------------------------------------------------------------------------------
 static void diag_fill(const swmhd_ctx *ctx, const double *r, swmhd_diag *o) {
     const swmhd_config &c = ctx->cfg;
     const double n = (double)c.Nx * (double)c.Ny, Lx = c.Nx * c.dx, Ly = c.Ny * c.dy;
@@ -353,24 +653,76 @@ static void diag_fill(const swmhd_ctx *ctx, const double *r, swmhd_diag *o) {
     o->all_finite = (r[8] == 0.0) ? 1 : 0; o->reserved = 0;
 }
 
+static inline bool diag_is_max(int q) { return q >= 4 && q <= 7; }
+
+// Slots [first, first+count) of every local slab -> `count` combined raw records on the host.
+// `reduce_ranks`: also combine across the processes of the ring (world > 1 with a communicator): two
+// ncclAllReduce (sum, max) on copies of the slot block.  Sums add in slab order (in-process) / NCCL order.
+static int fetch_diag(swmhd_ctx *ctx, int first, int count, bool reduce_ranks, std::vector<double> &out) {
+    const size_t nd = (size_t)count * NDIAG;
+    out.assign(nd, 0.0);
+    const bool xproc = reduce_ranks && ctx->cfg.world > 1 && ctx->comm_ready;
+    std::vector<double> tmp(2 * nd);
+    bool first_slab = true;
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        const double *src = s.d_diag + (size_t)first * NDIAG;
+        if (xproc) {
+            const NcclApi *api = nccl_api();
+            CK(cudaMemcpyAsync(s.d_red, src, nd * sizeof(double), cudaMemcpyDeviceToDevice, s.main));
+            CK(cudaMemcpyAsync(s.d_red + nd, src, nd * sizeof(double), cudaMemcpyDeviceToDevice, s.main));
+            NK(api->GroupStart());
+            NK(api->AllReduce(s.d_red, s.d_red, nd, ncclFloat64, ncclSum, s.comm, s.main));
+            NK(api->AllReduce(s.d_red + nd, s.d_red + nd, nd, ncclFloat64, ncclMax, s.comm, s.main));
+            NK(api->GroupEnd());
+            CK(cudaMemcpyAsync(tmp.data(), s.d_red, 2 * nd * sizeof(double), cudaMemcpyDeviceToHost, s.main));
+            CK(cudaStreamSynchronize(s.main));
+            for (size_t t = 0; t < nd; t++) out[t] = diag_is_max((int)(t % NDIAG)) ? tmp[nd + t] : tmp[t];
+        } else {
+            CK(cudaMemcpyAsync(tmp.data(), src, nd * sizeof(double), cudaMemcpyDeviceToHost, s.main));
+            CK(cudaStreamSynchronize(s.main));
+            for (size_t t = 0; t < nd; t++) {
+                const bool mx = diag_is_max((int)(t % NDIAG));
+                out[t] = first_slab ? tmp[t] : (mx ? fmax(out[t], tmp[t]) : out[t] + tmp[t]);
+            }
+        }
+        first_slab = false;
+    }
+    return SWMHD_OK;
+}
+
+static int diag_async(swmhd_ctx *ctx, Slab &s, int slot) {
+    const swmhd_config &c = ctx->cfg;
+    CK(cudaSetDevice(s.dev));
+    DiagParams d;
+    d.Nx = ctx->Nx; d.Ny = s.Ny; d.P = ctx->P; d.form = c.formulation;
+    d.dx = c.dx; d.dy = c.dy; d.g = c.g; d.h_ref = c.h_ref;
+    for (int k = 0; k < 4; k++) d.U[k] = s.U[ctx->cur][k];
+    d.partials = s.d_partials; d.nblocks = diag_blocks(ctx->Nx, s.Ny); d.stage = s.d_stage;
+    ctx->launches += 2;
+    CK(launch_diag(d, s.d_diag + (size_t)slot * NDIAG, s.main));
+    return SWMHD_OK;
+}
+
 extern "C" int swmhd_diagnostics(swmhd_ctx *ctx, swmhd_diag *out) {
     if (!ctx || !out) return SWMHD_ERR_ARG;
-    CK(cudaSetDevice(ctx->cfg.device));
-    int rc = diag_async(ctx, 0);
+    for (auto &s : ctx->slabs) { int rc = diag_async(ctx, s, 0); if (rc) return rc; }
+    std::vector<double> r;
+    int rc = fetch_diag(ctx, 0, 1, true, r);     // world > 1 without a communicator: this slab's partials
     if (rc) return rc;
-    double r[NDIAG];
-    CK(cudaMemcpyAsync(r, ctx->d_diag, sizeof r, cudaMemcpyDeviceToHost, ctx->main));
-    CK(cudaStreamSynchronize(ctx->main));
-    diag_fill(ctx, r, out);
+    diag_fill(ctx, r.data(), out);
     return out->all_finite ? SWMHD_OK : fail(ctx, SWMHD_ERR_NONFINITE, "state contains NaN/Inf");
 }
 
+// ---- stepping ---------------------------------------------------------------------------------------------
 static int step_impl(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags) {
     if (!ctx) return SWMHD_ERR_ARG;
     if (nsteps < 0) return fail(ctx, SWMHD_ERR_ARG, "nsteps < 0");
-    if (ctx->cfg.world != 1) return fail(ctx, SWMHD_ERR_STATE, "swmhd_step is single-slab; drive slabs with substage_edges/interior/finish");
-    CK(cudaSetDevice(ctx->cfg.device));
-    CK(cudaEventRecord(ctx->ev0, ctx->main));
+    if (ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "a host-driven substage is in flight");
+    if (ctx->last_stage != 0) return fail(ctx, SWMHD_ERR_STATE, "a step is in flight (finish its substages first)");
+    int rc = need_comm(ctx);
+    if (rc) return rc;
+    for (auto &s : ctx->slabs) { CK(cudaSetDevice(s.dev)); CK(cudaEventRecord(s.ev0, s.main)); }
     std::vector<double> host;
     int done = 0;
     while (done < nsteps) {
@@ -378,21 +730,26 @@ static int step_impl(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags) {
         if (diags && chunk > ctx->diag_slots) chunk = ctx->diag_slots;
         for (int n = 0; n < chunk; n++) {
             // diagnostics of the state at the start of the step: fused into the stage-1 kernel
-            for (int s = 1; s <= 3; s++) { int rc = substage_async(ctx, dt, s, nullptr, nullptr, diags ? n : -1); if (rc) return rc; }
+            for (int st = 1; st <= 3; st++) { rc = substage_async(ctx, dt, st, nullptr, nullptr, diags ? n : -1); if (rc) return rc; }
         }
         if (diags) {
-            host.resize((size_t)chunk * NDIAG);
-            CK(cudaMemcpyAsync(host.data(), ctx->d_diag, host.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
-            CK(cudaStreamSynchronize(ctx->main));
+            rc = fetch_diag(ctx, 0, chunk, true, host);
+            if (rc) return rc;
             for (int n = 0; n < chunk; n++) diag_fill(ctx, &host[(size_t)n * NDIAG], &diags[done + n]);
         }
         done += chunk;
     }
-    CK(cudaEventRecord(ctx->ev1, ctx->main));
-    CK(cudaStreamSynchronize(ctx->main));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms = ms;
+    float ms_max = 0;
+    for (auto &s : ctx->slabs) { CK(cudaSetDevice(s.dev)); CK(cudaEventRecord(s.ev1, s.main)); }
+    rc = sync_all(ctx);
+    if (rc) return rc;
+    for (auto &s : ctx->slabs) {
+        float ms = 0;
+        CK(cudaSetDevice(s.dev));
+        CK(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+        if (ms > ms_max) ms_max = ms;
+    }
+    ctx->last_ms = ms_max;
     return SWMHD_OK;
 }
 
@@ -404,75 +761,158 @@ extern "C" int swmhd_step_diag(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag
 
 // nsteps RK3 steps with a CUDA-event pair around every substage-kernel launch (on the
 // launching stream); out_ms[s] = mean device duration of the stage-(s+1) kernel.
-static int step_profile_impl(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3], bool with_diag);
-extern "C" int swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) { return step_profile_impl(ctx, dt, nsteps, out_ms, false); }
-extern "C" int swmhd_step_profile_diag(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) { return step_profile_impl(ctx, dt, nsteps, out_ms, true); }
 static int step_profile_impl(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3], bool with_diag) {
     if (!ctx || !out_ms) return SWMHD_ERR_ARG;
     if (nsteps < 1 || nsteps > 512) return fail(ctx, SWMHD_ERR_ARG, "nsteps must be in 1..512");
-    if (ctx->cfg.world != 1) return fail(ctx, SWMHD_ERR_STATE, "single-slab only");
-    CK(cudaSetDevice(ctx->cfg.device));
+    if (multi(ctx)) return fail(ctx, SWMHD_ERR_STATE, "single-slab only");
+    if (ctx->last_stage != 0 || ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "a step is in flight");
+    Slab &s = ctx->slabs[0];
+    CK(cudaSetDevice(s.dev));
     std::vector<cudaEvent_t> ev((size_t)nsteps * 6);
     for (auto &e : ev) CK(cudaEventCreate(&e));
     int rc = SWMHD_OK;
     for (int n = 0; n < nsteps && rc == SWMHD_OK; n++)
-        for (int s = 1; s <= 3 && rc == SWMHD_OK; s++)
-            rc = substage_async(ctx, dt, s, ev[(size_t)n * 6 + 2 * (s - 1)], ev[(size_t)n * 6 + 2 * (s - 1) + 1], with_diag ? (n % ctx->diag_slots) : -1);
+        for (int st = 1; st <= 3 && rc == SWMHD_OK; st++)
+            rc = substage_async(ctx, dt, st, ev[(size_t)n * 6 + 2 * (st - 1)], ev[(size_t)n * 6 + 2 * (st - 1) + 1], with_diag ? (n % ctx->diag_slots) : -1);
     if (rc == SWMHD_OK) {
-        CK(cudaStreamSynchronize(ctx->main));
-        for (int s = 0; s < 3; s++) {
+        CK(cudaStreamSynchronize(s.main));
+        for (int st = 0; st < 3; st++) {
             double acc = 0;
             for (int n = 0; n < nsteps; n++) {
                 float ms = 0;
-                CK(cudaEventElapsedTime(&ms, ev[(size_t)n * 6 + 2 * s], ev[(size_t)n * 6 + 2 * s + 1]));
+                CK(cudaEventElapsedTime(&ms, ev[(size_t)n * 6 + 2 * st], ev[(size_t)n * 6 + 2 * st + 1]));
                 acc += ms;
             }
-            out_ms[s] = acc / nsteps;
+            out_ms[st] = acc / nsteps;
         }
     }
     for (auto &e : ev) cudaEventDestroy(e);
     return rc;
 }
+extern "C" int swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) { return step_profile_impl(ctx, dt, nsteps, out_ms, false); }
+extern "C" int swmhd_step_profile_diag(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) { return step_profile_impl(ctx, dt, nsteps, out_ms, true); }
 
 extern "C" int swmhd_tendencies(swmhd_ctx *ctx, double *const G_host[4], size_t n_each) {
     if (!ctx || !G_host) return SWMHD_ERR_ARG;
-    (void)n_each;
-    CK(cudaSetDevice(ctx->cfg.device));
-    KParams p = kparams(ctx, 0.0, 0);
-    CK(launch_substage(ctx, p, 0, ctx->main));
+    if (multi(ctx)) return fail(ctx, SWMHD_ERR_STATE, "swmhd_tendencies is a single-slab test hook");
+    Slab &s = ctx->slabs[0];
     for (int k = 0; k < 4; k++) {
         if (!G_host[k]) return fail(ctx, SWMHD_ERR_ARG, "null G_host entry");
-        CK(cudaMemcpyAsync(G_host[k], ctx->G[k], ctx->len[k] * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
+        if (n_each < s.len[k]) return fail(ctx, SWMHD_ERR_ARG, "n_each is smaller than a field's parent array (v|vh has one row more in a Bounded-y grid)");
     }
-    CK(cudaStreamSynchronize(ctx->main));
+    if (ctx->last_stage != 0 || ctx->in_substage)
+        return fail(ctx, SWMHD_ERR_STATE, "tendencies overwrite G^-: call between steps, not after stage 1 or 2");
+    CK(cudaSetDevice(s.dev));
+    KParams p = kparams(ctx, s, 0.0, 0);
+    CK(launch_substage(ctx, p, 0, s.main));
+    for (int k = 0; k < 4; k++)
+        CK(cudaMemcpyAsync(G_host[k], s.G[k], s.len[k] * sizeof(double), cudaMemcpyDeviceToHost, s.main));
+    CK(cudaStreamSynchronize(s.main));
     return SWMHD_OK;
 }
 
-// u, v, s of the field writer, computed on the device from the current state.  The three results are
-// staged in the tendency buffers G[0..2] (free between steps: stage 1 never reads G^-), halos filled
-// like u-, v- and u-located fields, then copied to the host parent arrays.
+// ---- the field writer's outputs ---------------------------------------------------------------------------
+// u, v, s computed on the device from the current state into dst[0..2] (arrays shaped like u, v, u), halos
+// filled like u-, v- and u-located fields (x wrap + walls locally, y halos of a ring by exchange).
+static int compute_outputs(swmhd_ctx *ctx, bool staging) {
+    double *base[SWMHD_MAX_GPUS][4];
+    for (size_t si = 0; si < ctx->slabs.size(); si++) {
+        Slab &s = ctx->slabs[si];
+        CK(cudaSetDevice(s.dev));
+        double *const *dst = staging ? s.O : s.G;
+        OutputParams o;
+        o.Nx = ctx->Nx; o.Ny = s.Ny; o.P = ctx->P; o.form = ctx->cfg.formulation;
+        for (int k = 0; k < 4; k++) o.U[k] = s.U[ctx->cur][k];
+        o.out_u = dst[0]; o.out_v = dst[1]; o.out_s = dst[2];
+        ctx->launches++;
+        CK(launch_output(o, s.main));
+        double *outs[4] = {dst[0], dst[1], dst[2], dst[2]};
+        HaloParams h = halo_params(ctx, s, outs, 3, s.Ny + 2, true);
+        h.grad = 0;
+        h.rows[2] = s.rows[0]; h.rows[3] = s.rows[0];
+        ctx->launches++;
+        CK(launch_halo(h, s.main));
+        for (int k = 0; k < 4; k++) base[si][k] = outs[k];
+    }
+    if (multi(ctx) && ctx->comm_ready) return exchange(ctx, base, 3, false);
+    return SWMHD_OK;
+}
+
+static int copy_out(swmhd_ctx *ctx, Slab &s, double *host, const double *dev, int field, cudaStream_t st) {
+    if (!in_process_multi(ctx)) {
+        CK(cudaMemcpyAsync(host, dev, s.len[field] * sizeof(double), cudaMemcpyDeviceToHost, st));
+    } else {
+        int lo, hi;
+        gather_rows(ctx, s, field, &lo, &hi);
+        CK(cudaMemcpyAsync(host + (size_t)(s.j0 + lo) * ctx->P, dev + (size_t)lo * ctx->P,
+                           (size_t)(hi - lo) * ctx->P * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    return SWMHD_OK;
+}
+
 extern "C" int swmhd_get_outputs(swmhd_ctx *ctx, double *u_host, double *v_host, double *s_host) {
     if (!ctx || !u_host || !v_host || !s_host) return SWMHD_ERR_ARG;
-    if (ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "outputs can only be taken between steps");
-    CK(cudaSetDevice(ctx->cfg.device));
-    OutputParams o;
-    o.Nx = ctx->Nx; o.Ny = ctx->Ny; o.P = ctx->P; o.form = ctx->cfg.formulation;
-    for (int k = 0; k < 4; k++) o.U[k] = ctx->U[ctx->cur][k];
-    o.out_u = ctx->G[0]; o.out_v = ctx->G[1]; o.out_s = ctx->G[2];
-    ctx->launches++;
-    CK(launch_output(o, ctx->main));
-    if (ctx->cfg.world == 1) {          // periodic / wall halos of the outputs: (u, v, s) behave like (u, v, u)
-        double *outs[4] = {ctx->G[0], ctx->G[1], ctx->G[2], ctx->G[2]};
-        HaloParams h = halo_params(ctx, outs, 3, ctx->Ny + 2, true);
-        h.grad = 0;
-        h.rows[2] = ctx->rows[0]; h.rows[3] = ctx->rows[0];
-        ctx->launches++;
-        CK(launch_halo(h, ctx->main));
+    if (ctx->in_substage || ctx->last_stage != 0) return fail(ctx, SWMHD_ERR_STATE, "outputs can only be taken between steps (they stage through G^-)");
+    int rc = compute_outputs(ctx, false);
+    if (rc) return rc;
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        if ((rc = copy_out(ctx, s, u_host, s.G[0], SWMHD_U, s.main))) return rc;
+        if ((rc = copy_out(ctx, s, v_host, s.G[1], SWMHD_V, s.main))) return rc;
+        if ((rc = copy_out(ctx, s, s_host, s.G[2], SWMHD_U, s.main))) return rc;
     }
-    CK(cudaMemcpyAsync(u_host, ctx->G[0], ctx->len[0] * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
-    CK(cudaMemcpyAsync(v_host, ctx->G[1], ctx->len[1] * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
-    CK(cudaMemcpyAsync(s_host, ctx->G[2], ctx->len[0] * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
-    CK(cudaStreamSynchronize(ctx->main));
+    return sync_all(ctx);
+}
+
+extern "C" int swmhd_get_outputs_async(swmhd_ctx *ctx, double *u_host, double *v_host, double *s_host, double *A_host) {
+    if (!ctx || !u_host || !v_host || !s_host || !A_host) return SWMHD_ERR_ARG;
+    if (ctx->in_substage || ctx->last_stage != 0) return fail(ctx, SWMHD_ERR_STATE, "outputs can only be taken between steps");
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        const int shape[4] = {SWMHD_U, SWMHD_V, SWMHD_U, SWMHD_A};
+        for (int k = 0; k < 4; k++)
+            if (!s.O[k]) CK(cudaMalloc(&s.O[k], s.len[shape[k]] * sizeof(double)));
+        // the staging buffers may still be read by the previous asynchronous copy
+        if (s.out_in_flight) CK(cudaStreamWaitEvent(s.main, s.ev_out_done, 0));
+    }
+    int rc = compute_outputs(ctx, true);
+    if (rc) return rc;
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        CK(cudaMemcpyAsync(s.O[3], s.U[ctx->cur][SWMHD_A], s.len[SWMHD_A] * sizeof(double), cudaMemcpyDeviceToDevice, s.main));
+        CK(cudaEventRecord(s.ev_out_ready, s.main));
+        CK(cudaStreamWaitEvent(s.copy, s.ev_out_ready, 0));
+        if ((rc = copy_out(ctx, s, u_host, s.O[0], SWMHD_U, s.copy))) return rc;
+        if ((rc = copy_out(ctx, s, v_host, s.O[1], SWMHD_V, s.copy))) return rc;
+        if ((rc = copy_out(ctx, s, s_host, s.O[2], SWMHD_U, s.copy))) return rc;
+        if ((rc = copy_out(ctx, s, A_host, s.O[3], SWMHD_A, s.copy))) return rc;
+        CK(cudaEventRecord(s.ev_out_done, s.copy));
+        s.out_in_flight = true;
+    }
+    return SWMHD_OK;
+}
+
+extern "C" int swmhd_outputs_wait(swmhd_ctx *ctx) {
+    if (!ctx) return SWMHD_ERR_ARG;
+    for (auto &s : ctx->slabs) {
+        if (!s.out_in_flight) continue;
+        CK(cudaSetDevice(s.dev));
+        CK(cudaEventSynchronize(s.ev_out_done));
+        s.out_in_flight = false;
+    }
+    return SWMHD_OK;
+}
+
+extern "C" int swmhd_pin_host(void *ptr, size_t bytes) {
+    if (!ptr || !bytes) return SWMHD_ERR_ARG;
+    cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { g_create_err = std::string("cudaHostRegister: ") + cudaGetErrorString(e); cudaGetLastError(); return SWMHD_ERR_CUDA; }
+    return SWMHD_OK;
+}
+extern "C" int swmhd_unpin_host(void *ptr) {
+    if (!ptr) return SWMHD_ERR_ARG;
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { g_create_err = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); cudaGetLastError(); return SWMHD_ERR_CUDA; }
     return SWMHD_OK;
 }
 
@@ -487,17 +927,25 @@ extern "C" int64_t swmhd_launch_count(const swmhd_ctx *ctx) { return ctx ? ctx->
 extern "C" double swmhd_last_step_ms(const swmhd_ctx *ctx) { return ctx ? ctx->last_ms : NAN; }
 
 // ---------------------------------------------------------------------------
-// y-slab plumbing
+// host-driven exchange (a host that owns its own transport): one slab per context
+static int legacy_ok(swmhd_ctx *ctx) {
+    if (in_process_multi(ctx)) return fail(ctx, SWMHD_ERR_STATE, "n_gpus > 1 contexts exchange internally: use swmhd_step / swmhd_substage");
+    return SWMHD_OK;
+}
+
 extern "C" int swmhd_set_streams(swmhd_ctx *ctx, void *main_stream, void *edge_stream) {
     if (!ctx) return SWMHD_ERR_ARG;
-    CK(cudaSetDevice(ctx->cfg.device));
+    int rc = legacy_ok(ctx);
+    if (rc) return rc;
+    Slab &s = ctx->slabs[0];
+    CK(cudaSetDevice(s.dev));
     CK(cudaDeviceSynchronize());
-    if (ctx->own_streams) {
-        cudaStreamDestroy(ctx->main); cudaStreamDestroy(ctx->edge);
-        ctx->own_streams = false;
+    if (s.own_streams) {
+        cudaStreamDestroy(s.main); cudaStreamDestroy(s.edge);
+        s.own_streams = false;
     }
-    ctx->main = (cudaStream_t)main_stream;
-    ctx->edge = (cudaStream_t)edge_stream;
+    s.main = (cudaStream_t)main_stream;
+    s.edge = (cudaStream_t)edge_stream;
     return SWMHD_OK;
 }
 
@@ -505,42 +953,12 @@ extern "C" int swmhd_substage_edges(swmhd_ctx *ctx, double dt, int stage) {
     if (!ctx) return SWMHD_ERR_ARG;
     if (stage < 1 || stage > 3) return fail(ctx, SWMHD_ERR_ARG, "stage must be 1, 2 or 3");
     if (ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "previous substage not finished");
-    CK(cudaSetDevice(ctx->cfg.device));
-    // the edge stream may not overwrite rows the previous substage's kernels still read
-    CK(cudaEventRecord(ctx->ev_main, ctx->main));
-    CK(cudaStreamWaitEvent(ctx->edge, ctx->ev_main, 0));
-    KParams p = kparams(ctx, dt, stage);
-    ctx->pending_slot = -1;
-    if (stage == 1 && ctx->armed_slot >= 0) {
-        p.diag = ctx->d_partials;
-        ctx->pending_slot = ctx->armed_slot;
-        ctx->armed_slot = -1;
-    }
-    const int ntr = ctx->ntr, nl = ctx->n_last;
-    if (ntr <= 1 + nl) {            // slab too thin to split: everything is "edge"
-        CK(launch_substage(ctx, p, stage, ctx->edge));
-    } else {
-        p.tile_row0 = 0; p.tile_rows = 1;
-        CK(launch_substage(ctx, p, stage, ctx->edge));
-        p.tile_row0 = ntr - nl; p.tile_rows = nl;
-        CK(launch_substage(ctx, p, stage, ctx->edge));
-    }
-    // x wrap of the rows that are about to be sent, and wall BCs on end ranks
-    double *const *Un = ctx->U[1 - ctx->cur];
-    int ty = ctx->ty;
-    if (ntr <= 1 + nl) {
-        HaloParams h = halo_params(ctx, Un, 3, ctx->Ny + 2, true);
-        ctx->launches++;
-        CK(launch_halo(h, ctx->edge));
-    } else {
-        HaloParams h = halo_params(ctx, Un, 3, 3 + ty - 1, true);
-        ctx->launches++;
-        CK(launch_halo(h, ctx->edge));
-        HaloParams h2 = halo_params(ctx, Un, 3 + (ntr - nl) * ty, ctx->Ny + 2, false);
-        ctx->launches++;
-        CK(launch_halo(h2, ctx->edge));
-    }
-    CK(cudaEventRecord(ctx->ev_edge, ctx->edge));
+    int rc = legacy_ok(ctx);
+    if (rc) return rc;
+    rc = slab_edges(ctx, ctx->slabs[0], dt, stage, nullptr);
+    if (rc) return rc;
+    if (stage == 1) ctx->armed_slot = -1;
+    CK(cudaEventRecord(ctx->slabs[0].ev_edge, ctx->slabs[0].edge));
     ctx->in_substage = true;
     ctx->pending_dt = dt;
     return SWMHD_OK;
@@ -549,33 +967,17 @@ extern "C" int swmhd_substage_edges(swmhd_ctx *ctx, double dt, int stage) {
 extern "C" int swmhd_substage_interior(swmhd_ctx *ctx, double dt, int stage) {
     if (!ctx) return SWMHD_ERR_ARG;
     if (!ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "call swmhd_substage_edges first");
-    CK(cudaSetDevice(ctx->cfg.device));
-    const int ntr = ctx->ntr, nl = ctx->n_last;
-    if (ntr > 1 + nl) {
-        KParams p = kparams(ctx, dt, stage);
-        if (stage == 1 && ctx->pending_slot >= 0) p.diag = ctx->d_partials;
-        p.tile_row0 = 1; p.tile_rows = ntr - nl - 1;
-        CK(launch_substage(ctx, p, stage, ctx->main));
-        HaloParams h = halo_params(ctx, ctx->U[1 - ctx->cur], 3 + ctx->ty, 3 + (ntr - nl) * ctx->ty - 1, false);
-        ctx->launches++;
-        CK(launch_halo(h, ctx->main));
-    }
-    return SWMHD_OK;
+    return slab_interior(ctx, ctx->slabs[0], dt, stage);
 }
 
 extern "C" int swmhd_substage_finish(swmhd_ctx *ctx, int stage) {
     if (!ctx) return SWMHD_ERR_ARG;
     if (!ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "no substage in flight");
-    CK(cudaSetDevice(ctx->cfg.device));
-    CK(cudaStreamWaitEvent(ctx->main, ctx->ev_edge, 0));
-    if (ctx->pending_slot >= 0) {       // fold the per-tile partials of edges + interior (fixed order)
-        ctx->launches++;
-        CK(launch_diag_final(ctx->d_partials, ctx->ntiles, ctx->d_stage, ctx->d_diag + (size_t)ctx->pending_slot * NDIAG, ctx->main));
-        ctx->pending_slot = -1;
-    }
+    if (stage < 1 || stage > 3) return fail(ctx, SWMHD_ERR_ARG, "stage must be 1, 2 or 3");
+    int rc = slab_join(ctx, ctx->slabs[0], nullptr);
+    if (rc) return rc;
     ctx->cur = 1 - ctx->cur;
     ctx->in_substage = false;
-    if (stage < 1 || stage > 3) return fail(ctx, SWMHD_ERR_ARG, "stage must be 1, 2 or 3");
     tick(ctx, ctx->pending_dt, stage);
     return SWMHD_OK;
 }
@@ -583,10 +985,13 @@ extern "C" int swmhd_substage_finish(swmhd_ctx *ctx, int stage) {
 extern "C" int swmhd_exchange_rows(swmhd_ctx *ctx, int field, int which, void **dev_ptr, int *nrows, size_t *row_doubles) {
     if (!ctx || !dev_ptr || !nrows || !row_doubles) return SWMHD_ERR_ARG;
     if (field < 0 || field > 3 || which < 0 || which > 7) return fail(ctx, SWMHD_ERR_ARG, "bad field/which");
+    int rc = legacy_ok(ctx);
+    if (rc) return rc;
+    Slab &s = ctx->slabs[0];
     int buf = (which >= 4) ? ctx->cur : 1 - ctx->cur;   // 0-3: state being written, 4-7: current state
     int w = which & 3;
-    int row = (w == 0) ? 3 : (w == 1) ? ctx->Ny : (w == 2) ? 0 : ctx->Ny + 3;
-    *dev_ptr = (void *)(ctx->U[buf][field] + (size_t)row * ctx->P);
+    int row = (w == 0) ? 3 : (w == 1) ? s.Ny : (w == 2) ? 0 : s.Ny + 3;
+    *dev_ptr = (void *)(s.U[buf][field] + (size_t)row * ctx->P);
     *nrows = 3;
     *row_doubles = (size_t)ctx->P;
     return SWMHD_OK;
@@ -602,19 +1007,16 @@ extern "C" int swmhd_arm_diag(swmhd_ctx *ctx, int slot) {
 extern "C" int swmhd_get_diag_slots(swmhd_ctx *ctx, int first, int count, swmhd_diag *out) {
     if (!ctx || !out) return SWMHD_ERR_ARG;
     if (first < 0 || count < 0 || first + count > ctx->diag_slots) return fail(ctx, SWMHD_ERR_ARG, "diag slots out of range");
-    CK(cudaSetDevice(ctx->cfg.device));
-    std::vector<double> host((size_t)count * NDIAG);
-    CK(cudaStreamSynchronize(ctx->edge));
-    CK(cudaMemcpyAsync(host.data(), ctx->d_diag + (size_t)first * NDIAG, host.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->main));
-    CK(cudaStreamSynchronize(ctx->main));
+    int rc = sync_all(ctx);
+    if (rc) return rc;
+    std::vector<double> host;
+    rc = fetch_diag(ctx, first, count, false, host);     // this process's slabs only: the host combines ranks
+    if (rc) return rc;
     for (int n = 0; n < count; n++) diag_fill(ctx, &host[(size_t)n * NDIAG], &out[n]);
     return SWMHD_OK;
 }
 
 extern "C" int swmhd_sync(swmhd_ctx *ctx) {
     if (!ctx) return SWMHD_ERR_ARG;
-    CK(cudaSetDevice(ctx->cfg.device));
-    CK(cudaStreamSynchronize(ctx->edge));
-    CK(cudaStreamSynchronize(ctx->main));
-    return SWMHD_OK;
+    return sync_all(ctx);
 }

@@ -1,5 +1,6 @@
-"""y-slab domain decomposition: one process per GPU, halo rows exchanged with
-`torch.distributed` point-to-point ops (NCCL over NVLink on GPUs, gloo in CPU tests).
+"""y-slab domain decomposition, host side.  The exchange itself lives in libswmhd_cuda.so (ncclSend/ncclRecv,
+include/swmhd.h: swmhd_comm_init, n_gpus); this module holds the decomposition maths, the thin per-rank
+caller (`SlabModel`) and the host-driven route over `torch.distributed` point-to-point ops (gloo in CPU tests).
 
 The reference is single-process; the decomposition is the one its layout
 suggests: rank p owns global rows [j0+1, j0+ny] plus 3 halo rows on each side, stored
@@ -121,22 +122,35 @@ class SlabTimings:
 
 
 class SlabModel:
-    """One y-slab of the global grid on this process's GPU."""
+    """One y-slab of the global grid on this process's GPU (one process per GPU).
 
-    def __init__(self, cfg_global: abi.Config, rank=None, world=None, device=None):
+    Thin caller: the halo exchange (ncclSend/ncclRecv), the edge/interior stream overlap and the cross-rank
+    reductions of the diagnostics run inside libswmhd_cuda.so once the context holds a communicator.
+    torch.distributed only carries the NCCL unique id from rank 0 to the others (plumbing).
+    `host_exchange=True` keeps the host-driven path of the ABI instead (swmhd_substage_edges / exchange with
+    torch P2P ops / interior / finish): the route a host with its own transport would take.
+    """
+
+    def __init__(self, cfg_global: abi.Config, rank=None, world=None, device=None, host_exchange=False):
         from .context import Context
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         self.device = torch.cuda.current_device() if device is None else device
         self.cfg = slab_config(cfg_global, self.rank, self.world, self.device)
         self.periodic_y = cfg_global.topo_y == abi.PERIODIC
+        self.host_exchange = bool(host_exchange) and self.world > 1
         self.ctx = Context(self.cfg)
-        self.main = torch.cuda.Stream(device=self.device)
-        self.edge = torch.cuda.Stream(device=self.device, priority=-1)
-        self.ctx.set_streams(self.main.cuda_stream, self.edge.cuda_stream)
         self._views = {}
+        if self.host_exchange:
+            self.main = torch.cuda.Stream(device=self.device)
+            self.edge = torch.cuda.Stream(device=self.device, priority=-1)
+            self.ctx.set_streams(self.main.cuda_stream, self.edge.cuda_stream)
+        elif self.world > 1:
+            box = [self.ctx.comm_unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.ctx.comm_init(box[0])
 
-    # -- row views --------------------------------------------------------------------------
+    # -- host-driven exchange (legacy route) -------------------------------------------------
     def _rows(self, field, which):
         ptr, n, w = self.ctx.exchange_rows(field, which)
         t = self._views.get(ptr)
@@ -148,13 +162,20 @@ class SlabModel:
     def _exchange(self, current: bool, stream):
         off = CURRENT if current else 0
         rows_of = lambda f, which: self._rows(f, which + off)
-        if self.world == 1:
-            return []   # a single slab owns its own periodic wrap (done by the halo kernel)
         ops = exchange_ops(rows_of, self.rank, self.world, self.periodic_y)
         if not ops:
             return []
         with torch.cuda.stream(stream):
             return dist.batch_isend_irecv(ops)
+
+    def _host_substage(self, dt, stage):
+        self.ctx.substage_edges(dt, stage)
+        works = self._exchange(current=False, stream=self.edge)
+        self.ctx.substage_interior(dt, stage)
+        with torch.cuda.stream(self.main):
+            for w in works:
+                w.wait()
+        self.ctx.substage_finish(stage)
 
     # -- state ------------------------------------------------------------------------------
     def set_state(self, U_slab):
@@ -166,57 +187,41 @@ class SlabModel:
     def fill_halos(self):
         """update_state! after set!: x wrap / walls locally, y halos from the neighbours."""
         self.ctx.fill_halos()
-        works = self._exchange(current=True, stream=self.main)
-        with torch.cuda.stream(self.main):
-            for w in works:
-                w.wait()
-        self.main.synchronize()
+        if self.host_exchange:
+            works = self._exchange(current=True, stream=self.main)
+            with torch.cuda.stream(self.main):
+                for w in works:
+                    w.wait()
+            self.main.synchronize()
 
     # -- stepping ---------------------------------------------------------------------------
     def substage(self, dt, stage):
-        self.ctx.substage_edges(dt, stage)
-        works = self._exchange(current=False, stream=self.edge)
-        self.ctx.substage_interior(dt, stage)
-        with torch.cuda.stream(self.main):
-            for w in works:
-                w.wait()
-        self.ctx.substage_finish(stage)
+        if self.host_exchange:
+            self._host_substage(dt, stage)
+        else:
+            self.ctx.substage(dt, stage)
 
     def step(self, dt, nsteps=1):
+        if not self.host_exchange:
+            return self.ctx.step(dt, nsteps)
         for _ in range(nsteps):
             for stage in (1, 2, 3):
-                self.substage(dt, stage)
+                self._host_substage(dt, stage)
 
     def step_diag(self, dt, nsteps=1):
         """nsteps steps with the diagnostics of the state at the start of every step, fused into the
-        stage-1 kernels; one device->host copy and one small all_reduce for the whole batch."""
+        stage-1 kernels; one device->host copy and one small all-reduce for the whole batch."""
+        if not self.host_exchange:
+            return self.ctx.step_diag(dt, nsteps)
         assert nsteps <= 1024
         for n in range(nsteps):
             self.ctx.arm_diag(n)
             for stage in (1, 2, 3):
-                self.substage(dt, stage)
-        ds = self.ctx.get_diag_slots(0, nsteps)
-        if self.world == 1:
-            return ds
-        dev = f"cuda:{self.device}"
-        sums = torch.tensor([[d["ke"], d["me"], d["pe"], d["sum_h"], float(1 - d["all_finite"])] for d in ds], dtype=torch.float64, device=dev)
-        maxs = torch.tensor([[d["max_abs_u"], d["max_abs_A"], d["max_abs_div_hB"], -d["min_h"]] for d in ds], dtype=torch.float64, device=dev)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        dist.all_reduce(maxs, op=dist.ReduceOp.MAX)
-        out = []
-        for s, m in zip(sums.tolist(), maxs.tolist()):
-            out.append(dict(ke=s[0], me=s[1], pe=s[2], total=s[0] + s[1] + s[2], sum_h=s[3], all_finite=int(s[4] == 0),
-                            max_abs_u=m[0], max_abs_A=m[1], max_abs_div_hB=m[2], min_h=-m[3]))
-        return out
+                self._host_substage(dt, stage)
+        return [self._combine(d) for d in self.ctx.get_diag_slots(0, nsteps)]
 
-    def synchronize(self):
-        self.ctx.sync()
-
-    def diagnostics(self) -> dict:
+    def _combine(self, d):
         """Slab partials are already scaled by the global normalisation: sums add, extrema combine."""
-        d = self.ctx.diagnostics(check_finite=False)
-        if self.world == 1:
-            return d
         dev = f"cuda:{self.device}"
         sums = torch.tensor([d["ke"], d["me"], d["pe"], d["sum_h"], float(1 - d["all_finite"])], dtype=torch.float64, device=dev)
         maxs = torch.tensor([d["max_abs_u"], d["max_abs_A"], d["max_abs_div_hB"], -d["min_h"]], dtype=torch.float64, device=dev)
@@ -225,6 +230,17 @@ class SlabModel:
         s, m = sums.tolist(), maxs.tolist()
         return dict(ke=s[0], me=s[1], pe=s[2], total=s[0] + s[1] + s[2], sum_h=s[3], all_finite=int(s[4] == 0),
                     max_abs_u=m[0], max_abs_A=m[1], max_abs_div_hB=m[2], min_h=-m[3])
+
+    def synchronize(self):
+        self.ctx.sync()
+
+    @property
+    def last_step_ms(self):
+        return self.ctx.last_step_ms
+
+    def diagnostics(self) -> dict:
+        d = self.ctx.diagnostics(check_finite=False)       # with a communicator: already reduced over the ring
+        return self._combine(d) if self.host_exchange else d
 
     def close(self):
         self._views.clear()

@@ -36,9 +36,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_c(tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "swmhd.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "swmhd.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(swmhd_config), sizeof(swmhd_diag), offsetof(swmhd_config, dx), offsetof(swmhd_config, A_grad_south),'
-                   'offsetof(swmhd_config, slab_j0));return 0;}\n')
+                   'offsetof(swmhd_config, slab_j0), offsetof(swmhd_config, n_gpus), offsetof(swmhd_config, device_ids));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["/usr/bin/gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
@@ -47,6 +47,8 @@ def test_struct_layout_matches_c(tmp_path):
     assert int(out[2]) == abi.Config.dx.offset
     assert int(out[3]) == abi.Config.A_grad_south.offset
     assert int(out[4]) == abi.Config.slab_j0.offset
+    assert int(out[5]) == abi.Config.n_gpus.offset
+    assert int(out[6]) == abi.Config.device_ids.offset
 
 
 def test_no_cpu_fallback_and_argument_errors():
