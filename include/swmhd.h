@@ -74,7 +74,13 @@ enum {
     SWMHD_FLAG_WENO_JS        = 1 << 0, /* C1: JS weights instead of Z        */
     SWMHD_FLAG_PRESSURE_GHDH  = 1 << 1, /* C5: g*Ix(h)*dx(h) not dx(g h^2/2)  */
     SWMHD_FLAG_CDIVU_OVER_H   = 1 << 2, /* C6: A*div(uh,vh)/h                 */
-    SWMHD_FLAG_DIAG_CENTRED   = 1 << 3  /* C11: centre-averaged squares       */
+    SWMHD_FLAG_DIAG_CENTRED   = 1 << 3, /* C11: centre-averaged squares       */
+    /* C10 (Bounded-y wall semantics, SURVEY A.8 confidence L) — probed against the four published
+       Bounded-y figures by tools/probe_c10.py, table in DESIGN.md section 2 */
+    SWMHD_FLAG_BC_DEPTH1      = 1 << 4, /* no-flux / gradient BCs fill only the first halo row */
+    SWMHD_FLAG_WALL_WENO3     = 1 << 5, /* one cell further from the wall than the centred
+                                           fallback needs: WENO3 instead of centred 2nd order  */
+    SWMHD_FLAG_V_MIRROR       = 1 << 6  /* v|vh beyond the wall: odd mirror instead of untouched */
 };
 
 typedef struct swmhd_config {

@@ -173,6 +173,25 @@ static inline int ybuf(const S *s, int f, int n, int lo, int hi) {
 #define YC_HI(s) ((s)->Ny)
 #define YF_HI(s) ((s)->Ny + 1)
 
+/* WENO3 (C10 probe): left-biased value at the face between q[1] and q[2] from q[0..2] = psi[f-2], psi[f-1], psi[f];
+ * candidates (psi[f-1]+psi[f])/2 (C = 2/3) and (-psi[f-2]+3 psi[f-1])/2 (C = 1/3), Z or JS weights like WENO5. */
+static inline double weno3(const S *s, double a, double b, double c, double b0, double b1) {
+    double p0 = 0.5 * (b + c), p1 = 0.5 * (3.0 * b - a);
+    double a0, a1;
+    if (s->flags & SWMHD_FLAG_WENO_JS) {
+        a0 = (2.0 / 3.0) / ((b0 + s->eps) * (b0 + s->eps));
+        a1 = (1.0 / 3.0) / ((b1 + s->eps) * (b1 + s->eps));
+    } else {
+        double tau = fabs(b0 - b1), r0 = tau / (b0 + s->eps), r1 = tau / (b1 + s->eps);
+        a0 = (2.0 / 3.0) * (1.0 + r0 * r0);
+        a1 = (1.0 / 3.0) * (1.0 + r1 * r1);
+    }
+    return (a0 * p0 + a1 * p1) / (a0 + a1);
+}
+static inline void weno3_beta(double a, double b, double c, double *b0, double *b1) {
+    *b0 = (c - b) * (c - b); *b1 = (b - a) * (b - a);
+}
+
 /* left/right WENO5 values of F at x-face f of row j */
 static inline void weno_x(const S *s, fn2 F, int f, int j, double *L, double *R) {
     double q[5], r[5];
@@ -181,7 +200,15 @@ static inline void weno_x(const S *s, fn2 F, int f, int j, double *L, double *R)
 }
 /* left/right WENO5 values of F at y-face f of column i; valid elements lo..hi */
 static inline void weno_y(const S *s, fn2 F, int i, int f, int hi, double *L, double *R) {
-    if (ybuf(s, f, 3, 1, hi)) { *L = *R = sym2(F(s, i, f - 1), F(s, i, f)); return; }
+    if (ybuf(s, f, 3, 1, hi)) {
+        if ((s->flags & SWMHD_FLAG_WALL_WENO3) && !ybuf(s, f, 2, 1, hi)) {
+            double a = F(s, i, f - 2), b = F(s, i, f - 1), c = F(s, i, f), d = F(s, i, f + 1), b0, b1;
+            weno3_beta(a, b, c, &b0, &b1); *L = weno3(s, a, b, c, b0, b1);
+            weno3_beta(d, c, b, &b0, &b1); *R = weno3(s, d, c, b, b0, b1);
+            return;
+        }
+        *L = *R = sym2(F(s, i, f - 1), F(s, i, f)); return;
+    }
     double q[5], r[5];
     line_y(s, F, i, f, q, r);
     *L = weno(s, q); *R = weno(s, r);
@@ -330,7 +357,15 @@ static double Gu_vi(const S *s, int i, int j) { /* fcc */
     double vhat = ixy_fc(s, fV, i, j);
     double zL, zR;
     int f = j + 1; /* ζ along y, to the centre j  (→c convention = face f=j+1) */
-    if (ybuf(s, f, 3, 1, YF_HI(s))) {
+    if (ybuf(s, f, 3, 1, YF_HI(s)) && (s->flags & SWMHD_FLAG_WALL_WENO3) && !ybuf(s, f, 2, 1, YF_HI(s))) {
+        /* WENO3 with VelocityStencil smoothness: beta_k = (beta_k[ℑy u] + beta_k[ℑx v]) / 2 */
+        double z[4], uu[4], vv[4], bu0, bu1, bv0, bv1;
+        for (int k = 0; k < 4; k++) { z[k] = zeta(s, i, f - 2 + k); uu[k] = ut_ff(s, i, f - 2 + k); vv[k] = vt_ff(s, i, f - 2 + k); }
+        weno3_beta(uu[0], uu[1], uu[2], &bu0, &bu1); weno3_beta(vv[0], vv[1], vv[2], &bv0, &bv1);
+        zL = weno3(s, z[0], z[1], z[2], 0.5 * (bu0 + bv0), 0.5 * (bu1 + bv1));
+        weno3_beta(uu[3], uu[2], uu[1], &bu0, &bu1); weno3_beta(vv[3], vv[2], vv[1], &bv0, &bv1);
+        zR = weno3(s, z[3], z[2], z[1], 0.5 * (bu0 + bv0), 0.5 * (bu1 + bv1));
+    } else if (ybuf(s, f, 3, 1, YF_HI(s))) {
         zL = zR = sym2(zeta(s, i, f - 1), zeta(s, i, f));
     } else {
         double qz[5], rz[5], qu[5], ru[5], qv[5], rv[5];
@@ -457,9 +492,16 @@ static void fill_halo_field(const swmhd_config *c, double *a, int field) {
     } else if (field == SWMHD_V) {           /* impenetrable walls: v = 0 on j=1, Ny+1 */
         memset(ROW(1), 0, sizeof(double) * P);
         memset(ROW(Ny + 1), 0, sizeof(double) * P);
+        if (c->flags & SWMHD_FLAG_V_MIRROR)   /* C10 probe: odd mirror beyond the wall instead of untouched cells */
+            for (int k = 1; k <= 3; k++)
+                for (int x = 0; x < P; x++) {
+                    ROW(1 - k)[x] = -ROW(1 + k)[x];
+                    if (k <= 2) ROW(Ny + 1 + k)[x] = -ROW(Ny + 1 - k)[x];
+                }
     } else {                                  /* centre-located in y: mirror (+ gradient on A) */
         const int grad = (field == SWMHD_A && c->A_gradient_bc);
-        for (int k = 1; k <= 3; k++) {
+        const int depth = (c->flags & SWMHD_FLAG_BC_DEPTH1) ? 1 : 3;   /* C10 probe: deeper halo rows untouched */
+        for (int k = 1; k <= depth; k++) {
             double os = grad ? c->A_grad_south * (double)(2 * k - 1) * c->dy : 0.0;
             double on = grad ? c->A_grad_north * (double)(2 * k - 1) * c->dy : 0.0;
             for (int x = 0; x < P; x++) {

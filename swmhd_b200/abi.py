@@ -19,6 +19,7 @@ JACOBIAN, DIVERGENCE = 0, 1
 U, V, H, A = 0, 1, 2, 3
 ARITH_FAST, ARITH_STRICT = 0, 1
 FLAG_WENO_JS, FLAG_PRESSURE_GHDH, FLAG_CDIVU_OVER_H, FLAG_DIAG_CENTRED = 1, 2, 4, 8
+FLAG_BC_DEPTH1, FLAG_WALL_WENO3, FLAG_V_MIRROR = 16, 32, 64      # C10 probe (oracle only)
 HALO = 3
 
 

@@ -162,4 +162,56 @@ __device__ __forceinline__ void rcp_n(const double (&x)[N], double (&r)[N]) {
     FORN e[n] = fma(-x[n], r[n], 1.0);
     FORN r[n] = fma(r[n], e[n], r[n]);
 }
+
+// ---- round 2: cheaper forms of the same arithmetic (FAST mode only; differences are round-off) ----------
+// corr10_n: numerator and denominator of the WENO correction scaled by 10, so that the optimal weights
+// (3, 6, 1) and all but two of the candidate coefficients are FP64 immediates (no constant registers) and
+// two operations per reconstruction disappear:
+//     sum(w_k p_k) = c + [a0 (2 d3 - d4/2) + a1 (d2 + 2 d3) + a2 (5/6 d2 - 1/3 d1)] / [3 a0 + 6 a1 + a2]
+template <int N>
+__device__ __forceinline__ void corr10_n(const double (&d1)[N], const double (&d2)[N], const double (&d3)[N], const double (&d4)[N],
+                                         const double (&c0)[N], const double (&c1)[N], const double (&c2)[N],
+                                         double (&num)[N], double (&den)[N]) {
+    double tau[N], s0[N], s1[N], s2[N], q0[N], q1[N], q2[N], S[N], Z0[N], Z1[N], Z2[N];
+    FORN tau[n] = c2[n] - c0[n];
+    FORN s0[n] = c0[n] * c0[n];
+    FORN s1[n] = c1[n] * c1[n];
+    FORN s2[n] = c2[n] * c2[n];
+    FORN Z0[n] = -0.5 * d4[n];
+    FORN Z1[n] = fma(2.0, d3[n], d2[n]);                         // X1     = d2 + 2 d3
+    FORN Z2[n] = (-1.0 / 3.0) * d1[n];
+    FORN tau[n] = tau[n] * tau[n];
+    FORN q2[n] = s0[n] * s1[n];
+    FORN q0[n] = s1[n] * s2[n];
+    FORN q1[n] = s0[n] * s2[n];
+    FORN Z0[n] = fma(2.0, d3[n], Z0[n]);                         // X0 / 2 = 2 d3 - d4 / 2
+    FORN Z2[n] = fma(5.0 / 6.0, d2[n], Z2[n]);                   // X2 / 6 = 5/6 d2 - 1/3 d1
+    FORN S[n] = q2[n] * s2[n];
+    FORN q0[n] = fma(tau[n], q0[n], S[n]);                       // a0
+    FORN q1[n] = fma(tau[n], q1[n], S[n]);                       // a1
+    FORN q2[n] = fma(tau[n], q2[n], S[n]);                       // a2
+    FORN num[n] = q2[n] * Z2[n];
+    FORN den[n] = fma(6.0, q1[n], q2[n]);
+    FORN num[n] = fma(q1[n], Z1[n], num[n]);
+    FORN den[n] = fma(3.0, q0[n], den[n]);
+    FORN num[n] = fma(q0[n], Z0[n], num[n]);
+}
+// Reciprocals of mixed accuracy: entries [0, N1) get ONE Newton step after rcp.approx (relative error
+// ~1e-12: they divide a WENO correction that is itself O(dx^2)..O(1e-1) of the reconstructed value, the
+// result is within round-off of the two-step form), entries [N1, N) two steps (full precision: 1/h).
+template <int N, int N1>
+__device__ __forceinline__ void rcp_mix_n(const double (&x)[N], double (&r)[N]) {
+    double e[N];
+    FORN asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[n]) : "d"(x[n]));
+    FORN e[n] = fma(-x[n], r[n], 1.0);
+    FORN r[n] = fma(r[n], e[n], r[n]);
+#pragma unroll
+    for (int n = N1; n < N; n++) e[n] = fma(-x[n], r[n], 1.0);
+#pragma unroll
+    for (int n = N1; n < N; n++) r[n] = fma(r[n], e[n], r[n]);
+}
+// x > 0 from the sign and exponent word: an integer compare instead of an FP64-pipe DSETP.  Identical for
+// every normal x (positive denormals below 2^-1042 count as zero; they select the other upwind side of a
+// flux that is then multiplied by that denormal).
+__device__ __forceinline__ bool gt0(double x) { return __double2hiint(x) > 0; }
 } // namespace swmhd

@@ -21,6 +21,7 @@ struct KParams {
     int rows[4];         // parent rows per field (Ny+6, v: +1 when Bounded-y)
     double dx, dy, rdx, rdy, inv_az, g, f, eps;
     double dt, gam, zet, dtgam;  // stage coefficients; dtgam = dt*gam (stage 1)
+    double qrdxy;                // 0.25 / (dx dy): common factor of the telescoped Jacobian Lorentz force
     double dtzet;                // dt*zet (FAST arithmetic: U + (dtgam*Gn + dtzet*Gm) as two FMAs)
     double h_ref;                // h_i of the potential-energy diagnostic
     const double *Uo[4]; // state at the start of the substage (halos valid)

@@ -71,15 +71,16 @@ __device__ __forceinline__ bool ybuf(int by, int f, int n, int hi) { return by &
 // ---- WENO5-Z from shared memory (x direction): pointer-selected upwind stencil --------------------
 __device__ __forceinline__ double weno5_mem(const double *q, int s, double es) {
     const double a = q[0], b = q[s], c = q[2 * s], d = q[3 * s], e = q[4 * s];
-    const double d1 = b - a, d2 = c - b, d3 = d - c, d4 = e - d;
-    double c0 = es, c1 = es, c2 = es, num, den;
-    weno_beta_acc4(d1, d2, d3, d4, c0, c1, c2);
-    weno_corr4(d1, d2, d3, d4, c0, c1, c2, num, den);
-    return fma(num, frcp(den), c);
+    double d1[1] = {b - a}, d2[1] = {c - b}, d3[1] = {d - c}, d4[1] = {e - d};
+    double c0[1] = {es}, c1[1] = {es}, c2[1] = {es}, num[1], den[1], rc[1];
+    beta_acc_n<1>(d1, d2, d3, d4, c0, c1, c2);
+    corr10_n<1>(d1, d2, d3, d4, c0, c1, c2, num, den);
+    rcp_mix_n<1, 1>(den, rc);
+    return fma(num[0], rc[0], c);
 }
 // vel * psi_upwind at face f (ctr = &psi[f]): left-biased psi[f-3..f+1] for vel > 0, else the mirror
 __device__ __forceinline__ double upwind_weno_mem(const double *ctr, double vel, double eps) {
-    const bool pos = vel > 0.0;
+    const bool pos = gt0(vel);
     return vel * weno5_mem(pos ? ctr - 3 : ctr + 2, pos ? 1 : -1, eps * (12.0 / 13.0));
 }
 // first differences of the five upwind samples of a shared-memory line (pointer-selected side)
@@ -146,28 +147,42 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     mbar_wait(mbar, 0);
 
     // ---- A: derived staggered fields, each point once per tile --------------------------------------
+    {   // zeta, ℑy u, ℑx v at ffc: point q = (a, b) of the ZP-wide array, raw index r; both advanced incrementally
+        constexpr int DA = NT % ZP, DB = NT / ZP;
+        int a = tid % ZP, r = (tid / ZP + 1) * W + a + 1;
 #pragma unroll 4
-    for (int q = tid; q < NZ; q += NT) {                    // zeta, ℑy u, ℑx v at ffc
-        const int a = 1 + q % ZP, b = 1 + q / ZP;
-        const double vc = RAW(s_v, a, b), vw = RAW(s_v, a - 1, b), uc = RAW(s_u, a, b), us = RAW(s_u, a, b - 1);
-        s_z[q] = fma(vc - vw, p.rdx, (us - uc) * p.rdy);
-        s_ut[q] = 0.5 * (us + uc);
-        s_vt[q] = 0.5 * (vw + vc);
+        for (int q = tid; q < NZ; q += NT) {
+            const double vc = s_v[r], vw = s_v[r - 1], uc = s_u[r], us = s_u[r - W];
+            s_z[q] = fma(vc - vw, p.rdx, (us - uc) * p.rdy);
+            s_ut[q] = 0.5 * (us + uc);
+            s_vt[q] = 0.5 * (vw + vc);
+            a += DA; r += DB * W + DA;
+            if (a >= ZP) { a -= ZP; r += W - ZP; }
+        }
     }
+    {   // Bx, By at ccc (sw_mhd_jacobian_functions.jl:1-7)
+        constexpr int DA = NT % CP, DB = NT / CP;
+        int a = tid % CP, r = (tid / CP + 2) * W + a + 2;
+        const double hry = 0.5 * p.rdy, hrx = 0.5 * p.rdx;
 #pragma unroll 3
-    for (int q = tid; q < NC; q += NT) {                    // Bx, By at ccc (sw_mhd_jacobian_functions.jl:1-7)
-        const int a = 2 + q % CP, b = 2 + q / CP;
-        const double rh = frcp(RAW(s_h, a, b));
-        s_Bx[q] = ((RAW(s_A, a, b - 1) - RAW(s_A, a, b + 1)) * (0.5 * p.rdy)) * rh;
-        s_By[q] = ((RAW(s_A, a + 1, b) - RAW(s_A, a - 1, b)) * (0.5 * p.rdx)) * rh;
+        for (int q = tid; q < NC; q += NT) {
+            const double rh = frcp(s_h[r]);
+            s_Bx[q] = ((s_A[r - W] - s_A[r + W]) * hry) * rh;
+            s_By[q] = ((s_A[r + 1] - s_A[r - 1]) * hrx) * rh;
+            a += DA; r += DB * W + DA;
+            if (a >= CP) { a -= CP; r += W - CP; }
+        }
     }
     __syncthreads();
 
     // ---- B/C: warp-private from here on --------------------------------------------------------------
 
+    // warps of a ragged last tile row (or of an 8-row edge strip) that own no cell skip the row walk
+    const bool warp_has_rows = (jc0 <= p.row_end);
+
     // B0: the tile's east column of x faces for this warp's rows: lanes 0..R-1 take h, lanes R..2R-1 take A
     double eastF = 0.0;
-    if (lane < 2 * R) {
+    if (warp_has_rows && lane < 2 * R) {
         const int b = lj0 + (lane & (R - 1));
         const double *arr = (lane < R) ? s_h : s_A;
         eastF = upwind_weno_mem(&RAW(arr, TX + 3, b), RAW(s_u, TX + 3, b), eps);
@@ -177,54 +192,37 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     // row; every other iteration evaluates the NORTH face lj+1 of its row and keeps it for the next one.
     double vC = RAW(s_v, li, lj0 - 1), vW = RAW(s_v, li - 1, lj0 - 1);
     double fyh_s = 0.0, fyA_s = 0.0, K_s = 0.0;
-    double dg[NDIAG];
-    if constexpr (DIAG) {
-#pragma unroll
-        for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
-        dg[6] = -INFINITY;
-    }
-    (void)dg;
+    const double es1 = eps * (12.0 / 13.0), es2 = eps * (24.0 / 13.0);
+    const bool col_ok = (i <= Nx);
+    size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(jc0 + 1);   // cell (i, jc0 - 1): advanced by one row per iteration
 
 #pragma unroll 1
-    for (int it = -1; it < R; ++it) {
+    for (int it = warp_has_rows ? -1 : R; it < R; ++it) {
         const int lj = lj0 + it;
         const int j = jc0 + it, gj = gj0 + it;
-        const bool active = (i <= Nx) && (j <= p.row_end);
-        const size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(j + 2);
-        // G^- of this row was requested one iteration ago (row 0: before the tile wait); request the next row
-        const double Gm0 = Gq0, Gm1 = Gq1, Gm2 = Gq2, Gm3 = Gq3;
-        if constexpr (STAGE >= 2) {
-            if (it >= 0 && it + 1 < R && (i <= Nx) && (j + 1 <= p.row_end)) {
-                const size_t gn = gcell + (size_t)P;
-                Gq0 = p.G[0][gn]; Gq1 = p.G[1][gn]; Gq2 = p.G[2][gn]; Gq3 = p.G[3][gn];
-            }
-        }
+        const bool active = col_ok && (j <= p.row_end);
         const double vN = RAW(s_v, li, lj + 1), vWn = RAW(s_v, li - 1, lj + 1);
-        const bool posN = vN > 0.0, bufN = ybuf(p.by, gj + 1, 3, p.NyG);
-        const double es1 = eps * (12.0 / 13.0), es2 = eps * (24.0 / 13.0);
+        const bool posN = gt0(vN);
         double fyh_n, fyA_n;
         const double *const ph = &RAW(s_h, li, lj + 1), *const pA = &RAW(s_A, li, lj + 1);   // north face lj+1
         // kinetic energy K at ccc (li, lj), in registers: the row walk keeps it as the next row's K(li, lj-1)
         // (a phase-A array of K would push the tile over the shared memory of 4 CTAs per SM)
-        const double uwk = RAW(s_u, li, lj), uek = RAW(s_u, li + 1, lj);
-        const double Kc = 0.25 * (fma(uwk, uwk, uek * uek) + fma(vC, vC, vN * vN));
+        const double uw = RAW(s_u, li, lj), ue = RAW(s_u, li + 1, lj);
+        const double Kc = 0.25 * (fma(uw, uw, ue * ue) + fma(vC, vC, vN * vN));
         if (it < 0) {
             // south face of the warp's first row: h and A fluxes
             double d1[2], d2[2], d3[2], d4[2], c0[2] = {es1, es1}, c1[2] = {es1, es1}, c2[2] = {es1, es1}, num[2], den[2], rc[2];
             double ch, cA;
             UPDC(posN, ph, W, 0, ch); UPDC(posN, pA, W, 1, cA);
             beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
-            corr_n<2>(d1, d2, d3, d4, c0, c1, c2, num, den);
-            rcp_n<2>(den, rc);
-            const double wh_ = vN * fma(num[0], rc[0], ch);
-            const double wA_ = vN * fma(num[1], rc[1], cA);
-            fyh_n = bufN ? vN * sym2(ph[-W], ph[0]) : wh_;
-            fyA_n = bufN ? vN * sym2(pA[-W], pA[0]) : wA_;
+            corr10_n<2>(d1, d2, d3, d4, c0, c1, c2, num, den);
+            rcp_mix_n<2, 2>(den, rc);
+            fyh_n = vN * fma(num[0], rc[0], ch);
+            fyA_n = vN * fma(num[1], rc[1], cA);
         } else {
             const double vhat = avg4(vW, vC, vWn, vN);
-            const double uw = RAW(s_u, li, lj), ue = RAW(s_u, li + 1, lj);
             const double uhat = avg4(RAW(s_u, li, lj - 1), RAW(s_u, li + 1, lj - 1), uw, ue);
-            const bool posv = vhat > 0.0, posu = uhat > 0.0, posx = uw > 0.0;
+            const bool posv = gt0(vhat), posu = gt0(uhat), posx = gt0(uw);
             const int offx = (lj - 1) * ZP + (posu ? li - 2 : li + 3) - 1;   // zeta to the centre i along x
             const int sx = posu ? 1 : -1;
             const double *qh = posx ? &RAW(s_h, li - 3, lj) : &RAW(s_h, li + 2, lj);
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
                 UPD(posv, pv, ZP, 0); diffs_mem(s_vt + offx, sx, d1[1], d2[1], d3[1], d4[1]);
                 beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
                 UPDC(posv, pz, ZP, 0, cz0); diffs_mem(s_z + offx, sx, d1[1], d2[1], d3[1], d4[1], cz1);
-                corr_n<2>(d1, d2, d3, d4, c0, c1, c2, num2, den);
+                corr10_n<2>(d1, d2, d3, d4, c0, c1, c2, num2, den);
                 rc[0] = den[0]; rc[1] = den[1];
             }
             {   // flux quartet: h, A through the north face, h, A through the west face
@@ -249,7 +247,7 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
                 diffs_mem(qh, sp, d1[2], d2[2], d3[2], d4[2], ch2);
                 diffs_mem(qA, sp, d1[3], d2[3], d3[3], d4[3], cA3);
                 beta_acc_n<4>(d1, d2, d3, d4, c0, c1, c2);
-                corr_n<4>(d1, d2, d3, d4, c0, c1, c2, num4, den);
+                corr10_n<4>(d1, d2, d3, d4, c0, c1, c2, num4, den);
                 rc[2] = den[0]; rc[3] = den[1]; rc[4] = den[2]; rc[5] = den[3];
             }
             const double hc = ph[-W], hw_ = RAW(s_h, li - 1, lj), hs = RAW(s_h, li, lj - 1);
@@ -259,18 +257,14 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
                 double x[8];
 #pragma unroll
                 for (int n = 0; n < 8; n++) x[n] = rc[n];
-                rcp_n<8>(x, rc);
+                rcp_mix_n<8, 6>(x, rc);                                 // six WENO denominators, two face depths
             }
-            const double zy = fma(num2[0], rc[0], cz0);
-            const double zx = fma(num2[1], rc[1], cz1);
-            const double wh_ = vN * fma(num4[0], rc[2], ch0);
-            const double wA_ = vN * fma(num4[1], rc[3], cA1);
+            fyh_n = vN * fma(num4[0], rc[2], ch0);
+            fyA_n = vN * fma(num4[1], rc[3], cA1);
             const double fxh = uw * fma(num4[2], rc[4], ch2);
             const double fxA = uw * fma(num4[3], rc[5], cA3);
-            fyh_n = bufN ? vN * sym2(hc, ph[0]) : wh_;
-            fyA_n = bufN ? vN * sym2(pA[-W], pA[0]) : wA_;
-            const double adv_u = vhat * (ybuf(p.by, gj + 1, 3, p.NyG + 1) ? sym2(pz[-ZP], pz[0]) : zy);
-            const double adv_v = uhat * zx;
+            double adv_u = vhat * fma(num2[0], rc[0], cz0);
+            const double adv_v = uhat * fma(num2[1], rc[1], cz1);
             // east faces: the neighbour lane's west face; lane 31 takes the pre-pass value
             double fxh_e = __shfl_down_sync(0xffffffffu, fxh, 1), fxA_e = __shfl_down_sync(0xffffffffu, fxA, 1);
             const double eh = __shfl_sync(0xffffffffu, eastF, it), eA = __shfl_sync(0xffffffffu, eastF, R + it);
@@ -280,51 +274,64 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
             const double Ac = pA[-W], An = pA[0], As = RAW(s_A, li, lj - 1);
             const double Aw = RAW(s_A, li - 1, lj), Awn = RAW(s_A, li - 1, lj + 1), Aws = RAW(s_A, li - 1, lj - 1);
             {   // Gu at fcc — lorentz_force_func_x, sw_mhd_jacobian_functions.jl:10-13,20-22 — and
-                // Gv at cfc — lorentz_force_func_y, :15-18,24-26 — advanced together
+                // Gv at cfc — lorentz_force_func_y, :15-18,24-26 — advanced together.
+                // ℑxy(∂y F) telescopes to (F(i-1,j+1) + F(i,j+1) - F(i-1,j-1) - F(i,j-1)) / (4 dy); the common
+                // factor 1/(4 dx dy) of both Jacobians multiplies the reciprocal depth once.
                 const double uww = RAW(s_u, li - 1, lj);
                 const double Kw = 0.25 * (fma(uww, uww, uw * uw) + fma(vW, vW, vWn * vWn)); // K at ccc (li-1, lj)
-                const double dKx = (Kc - Kw) * p.rdx;
-                const double dKy = (Kc - K_s) * p.rdy;
-                const double pgx = p.g * ((hc - hw_) * p.rdx);
-                const double pgy = p.g * ((hc - hs) * p.rdy);
-                const double dxA = (Ac - Aw) * p.rdx;
-                const double dyA = (Ac - As) * p.rdy;
-                // ℑxy(∂y F) telescopes to (F(i-1,j+1) + F(i,j+1) - F(i-1,j-1) - F(i,j-1)) / (4 dy)
-                const double m1x = ((Cc(s_Bx, li - 1, lj + 1) + Cc(s_Bx, li, lj + 1)) - (Cc(s_Bx, li - 1, lj - 1) + Cc(s_Bx, li, lj - 1))) * (0.25 * p.rdy);
-                const double m1y = ((RAW(s_A, li + 1, lj - 1) + RAW(s_A, li + 1, lj)) - (Aws + Aw)) * (0.25 * p.rdx);
-                const double m2x = ((Awn + An) - (Aws + As)) * (0.25 * p.rdy);
-                const double m2y = ((Cc(s_By, li + 1, lj - 1) + Cc(s_By, li + 1, lj)) - (Cc(s_By, li - 1, lj - 1) + Cc(s_By, li - 1, lj))) * (0.25 * p.rdx);
-                const double jacx = fma(dxA, m1x, -(m2x * ((Cc(s_Bx, li, lj) - Cc(s_Bx, li - 1, lj)) * p.rdx)));
-                const double jacy = fma(m1y, (Cc(s_By, li, lj) - Cc(s_By, li, lj - 1)) * p.rdy, -(dyA * m2y));
-                Gn0 = fma(jacx, rc[6], fma(p.f, vhat, (adv_u - dKx) - pgx));
-                Gn1 = fma(jacy, rc[7], fma(-p.f, uhat, (-adv_v - dKy) - pgy));
-                if (p.by && gj < 2) Gn1 = 0.0;                          // wall rows of a Bounded-y grid keep v = 0
+                const double S1x = (Cc(s_Bx, li - 1, lj + 1) + Cc(s_Bx, li, lj + 1)) - (Cc(s_Bx, li - 1, lj - 1) + Cc(s_Bx, li, lj - 1));
+                const double S1y = (RAW(s_A, li + 1, lj - 1) + RAW(s_A, li + 1, lj)) - (Aws + Aw);
+                const double S2x = (Awn + An) - (Aws + As);
+                const double S2y = (Cc(s_By, li + 1, lj - 1) + Cc(s_By, li + 1, lj)) - (Cc(s_By, li - 1, lj - 1) + Cc(s_By, li - 1, lj));
+                const double jx = fma(Ac - Aw, S1x, -(S2x * (Cc(s_Bx, li, lj) - Cc(s_Bx, li - 1, lj))));
+                const double jy = fma(S1y, Cc(s_By, li, lj) - Cc(s_By, li, lj - 1), -((Ac - As) * S2y));
+                // -dx(K + g h), -dy(K + g h)
+                const double tx = fma(p.g, hc - hw_, Kc - Kw);
+                const double ty = fma(p.g, hc - hs, Kc - K_s);
+                // Bounded-y: centred second order within the wall buffers (oracle ybuf), v = 0 on the wall rows
+                if (p.by && ybuf(1, gj + 1, 3, p.NyG + 1)) adv_u = vhat * sym2(pz[-ZP], pz[0]);
+                Gn0 = fma(jx, rc[6] * p.qrdxy, fma(p.f, vhat, fma(-p.rdx, tx, adv_u)));
+                Gn1 = fma(jy, rc[7] * p.qrdxy, fma(-p.f, uhat, fma(-p.rdy, ty, -adv_v)));
+                if (p.by && gj < 2) Gn1 = 0.0;
             }
+            if (p.by && ybuf(1, gj + 1, 3, p.NyG)) { fyh_n = vN * sym2(hc, ph[0]); fyA_n = vN * sym2(Ac, An); }
             {   // Gh, GA at ccc: flux divergences (metric factors folded in: Ax/Az = 1/dx, Ay/Az = 1/dy)
                 Gn2 = -fma(fxh_e - fxh, p.rdx, (fyh_n - fyh_s) * p.rdy);
                 const double d = fma(fxA_e - fxA, p.rdx, (fyA_n - fyA_s) * p.rdy);
                 const double dv = fma(ue - uw, p.rdx, (vN - vC) * p.rdy);
-                Gn3 = -d + Ac * dv;
+                Gn3 = fma(Ac, dv, -d);
             }
             // ---- RK3 substep + stores --------------------------------------------------------------
             if (active) {
                 const double Gn[4] = {Gn0, Gn1, Gn2, Gn3};
-                const double Gm[4] = {Gm0, Gm1, Gm2, Gm3};
+                const double Gm[4] = {Gq0, Gq1, Gq2, Gq3};
                 const double Uc[4] = {uw, vC, hc, Ac};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     if constexpr (STAGE == 1) {
-                        p.Un[k][gcell] = Uc[k] + p.dtgam * Gn[k];
+                        p.Un[k][gcell] = fma(p.dtgam, Gn[k], Uc[k]);
                         p.G[k][gcell] = Gn[k];
                     } else {
-                        p.Un[k][gcell] = Uc[k] + p.dt * (p.gam * Gn[k] + p.zet * Gm[k]);
+                        p.Un[k][gcell] = fma(p.dtgam, Gn[k], fma(p.dtzet, Gm[k], Uc[k]));
                         if constexpr (STAGE == 2) p.G[k][gcell] = Gn[k];
                     }
                 }
             }
+            // G^- of the next row: requested now, consumed at the end of the next iteration (the first row's was
+            // requested before the tile wait)
+            if constexpr (STAGE >= 2) {
+                if (it + 1 < R && col_ok && (j + 1 <= p.row_end)) {
+                    const size_t gn = gcell + (size_t)P;
+                    Gq0 = p.G[0][gn]; Gq1 = p.G[1][gn]; Gq2 = p.G[2][gn]; Gq3 = p.G[3][gn];
+                }
+            }
+        }
+        if (it < 0 && p.by && ybuf(1, gj + 1, 3, p.NyG)) {     // south face of the first row inside a wall buffer
+            fyh_n = vN * sym2(ph[-W], ph[0]); fyA_n = vN * sym2(pA[-W], pA[0]);
         }
         // slide to the next row
         fyh_s = fyh_n; fyA_s = fyA_n; K_s = Kc; vC = vN; vW = vWn;
+        gcell += (size_t)P;
     }
 
     // ---- fused diagnostics of the state at the start of the step --------------------------
@@ -332,6 +339,10 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     // its R cells from the raw tile (2R+3 reciprocals advanced together), the east neighbours come by
     // shuffle, the tile's east column from lanes 0..R+1.
     if constexpr (DIAG) {
+        double dg[NDIAG];
+#pragma unroll
+        for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
+        dg[6] = -INFINITY;
         double *const s_red = smem + DERIVED + 2;            // NW x NDIAG partials (behind the mbarrier word)
         constexpr int NR = R + 2;                            // rows b = lj0-1 .. lj0+R, index k = b - (lj0-1)
         auto sq = [](double x) { return x * x; };
@@ -348,7 +359,19 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
             for (int k = 0; k < NR; k++) den[k] = 0.5 * (hwst[k] + hcol[k]);                 // ℑx h at fcc(li, b)
 #pragma unroll
             for (int k = 1; k < NR; k++) den[NR + k - 1] = 0.5 * (hcol[k - 1] + hcol[k]);     // ℑy h at cfc(li, b)
-            rcp_n<2 * NR - 1>(den, rc);
+            {   // two batches: eleven reciprocals in flight at once do not fit the register budget of 4 CTAs per SM
+                double xa[NR], ra[NR], xb[NR - 1], rb[NR - 1];
+#pragma unroll
+                for (int k = 0; k < NR; k++) xa[k] = den[k];
+                rcp_n<NR>(xa, ra);
+#pragma unroll
+                for (int k = 0; k < NR; k++) rc[k] = ra[k];
+#pragma unroll
+                for (int k = 0; k < NR - 1; k++) xb[k] = den[NR + k];
+                rcp_n<NR - 1>(xb, rb);
+#pragma unroll
+                for (int k = 0; k < NR - 1; k++) rc[NR + k] = rb[k];
+            }
 #pragma unroll
             for (int k = 0; k < NR; k++) sqy[k] = sq(((Ac[k] - Aw[k]) * p.rdx) * rc[k]);      // (dxA / ℑx h)^2
             sqx[0] = 0.0;
@@ -517,20 +540,33 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
     mbar_wait(mbar, 0);
 
     // ---- A: hBx, hBy, Bx, By (sw_mhd_divergence_functions.jl:134-148) and the reciprocal depths ---------
+    {   // point t = (a, b) of the BP-wide arrays, raw index r; both advanced incrementally
+        constexpr int DA = NT % BP, DB = NT / BP;
+        int a = tid % BP, r = (tid / BP + 1) * W + a + 1;
+        const double qy = 0.25 * p.rdy, qx = 0.25 * p.rdx;
 #pragma unroll 2
-    for (int t = tid; t < NB; t += NT) {
-        const int a = 1 + t % BP, b = 1 + t / BP;
-        // telescoped ℑxy∂: hBx = -(ℑxy ∂y A), hBy = ℑxy ∂x A
-        const double hbx = ((RAW(s_A, a - 1, b - 1) + RAW(s_A, a, b - 1)) - (RAW(s_A, a - 1, b + 1) + RAW(s_A, a, b + 1))) * (0.25 * p.rdy);
-        const double hby = ((RAW(s_A, a + 1, b - 1) + RAW(s_A, a + 1, b)) - (RAW(s_A, a - 1, b - 1) + RAW(s_A, a - 1, b))) * (0.25 * p.rdx);
-        const double hc = RAW(s_h, a, b);
-        const double rhx = frcp(0.5 * (RAW(s_h, a - 1, b) + hc)), rhy = frcp(0.5 * (RAW(s_h, a, b - 1) + hc));
-        s_hBx[t] = hbx; s_hBy[t] = hby;
-        s_Bx[t] = hbx * rhx; s_By[t] = hby * rhy;
+        for (int t = tid; t < NB; t += NT) {
+            // telescoped ℑxy∂: hBx = -(ℑxy ∂y A), hBy = ℑxy ∂x A
+            const double Asw = s_A[r - W - 1], As = s_A[r - W], Aw = s_A[r - 1];
+            const double hbx = ((Asw + As) - (s_A[r + W - 1] + s_A[r + W])) * qy;
+            const double hby = ((s_A[r - W + 1] + s_A[r + 1]) - (Asw + Aw)) * qx;
+            const double hc = s_h[r];
+            double x2[2] = {0.5 * (s_h[r - 1] + hc), 0.5 * (s_h[r - W] + hc)}, r2[2];
+            rcp_n<2>(x2, r2);
+            s_hBx[t] = hbx; s_hBy[t] = hby;
+            s_Bx[t] = hbx * r2[0]; s_By[t] = hby * r2[1];
+            a += DA; r += DB * W + DA;
+            if (a >= BP) { a -= BP; r += W - BP; }
+        }
     }
-    for (int q = tid; q < NRH; q += NT) {
-        const int a = 2 + q % RP, b = 2 + q / RP;
-        s_rh[q] = frcp(RAW(s_h, a, b));
+    {
+        constexpr int DA = NT % RP, DB = NT / RP;
+        int a = tid % RP, r = (tid / RP + 2) * W + a + 2;
+        for (int q = tid; q < NRH; q += NT) {
+            s_rh[q] = frcp(s_h[r]);
+            a += DA; r += DB * W + DA;
+            if (a >= RP) { a -= RP; r += W - RP; }
+        }
     }
     __syncthreads();
 
@@ -538,44 +574,29 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
     const double es = eps * (12.0 / 13.0);
     double Fvu_s = 0.0, Fvv_s = 0.0, Ty_s = 0.0, vq_s = 0.0;   // south side of the current row (from the previous iteration)
     double rhff_s = 0.0;                                       // 1/ℑxy h at the ffc point (li, lj), likewise
-    double dg[NDIAG];
-    if constexpr (DIAG) {
-#pragma unroll
-        for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
-        dg[6] = -INFINITY;
-    }
-    (void)dg;
+    const bool warp_has_rows = (jc0 <= p.row_end);             // ragged last tile row / 8-row edge strips
+    size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(jc0 + 1);   // cell (i, jc0 - 1): one row further per iteration
 
 #pragma unroll 1
-    for (int it = -1; it < R; ++it) {
+    for (int it = warp_has_rows ? -1 : R; it < R; ++it) {
         const int lj = lj0 + it, ln = lj + 1;               // current row, north face row
         const int j = jc0 + it, gj = gj0 + it;
         const bool active = own && (j <= p.row_end);
-        const size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(j + 2);
-        const double Gm0 = Gq0, Gm1 = Gq1, Gm2 = Gq2, Gm3 = Gq3;
-        if constexpr (STAGE >= 2) {
-            if (it >= 0 && it + 1 < R && own && (j + 1 <= p.row_end)) {
-                const size_t gn = gcell + (size_t)P;
-                Gq0 = p.G[0][gn]; Gq1 = p.G[1][gn]; Gq2 = p.G[2][gn]; Gq3 = p.G[3][gn];
-            }
-        }
         // ---- north side: F_vu - Lyx at ffc (li, ln), F_vv - Lyy at ccc (li, lj), tracer flux at cfc (li, ln) ----
         double Fvu_n, Fvv_c, Ty_n, vq_n, rhff_n;
         {
             const double vln = RAW(s_v, li, ln);
             double vel[3];
             vel[0] = sym4(RAW(s_v, li - 2, ln), RAW(s_v, li - 1, ln), vln, RAW(s_v, li + 1, ln));
-            {
-                const double vc = RAW(s_v, li, lj);
-                const double v2 = sym2(vc, vln), v4 = sym4(RAW(s_v, li, lj - 1), vc, vln, RAW(s_v, li, lj + 2));
-                vel[1] = ybuf(by, gj + 1, 2, NyG + 1) ? v2 : v4;
-            }
+            const double vc = RAW(s_v, li, lj);
+            vel[1] = sym4(RAW(s_v, li, lj - 1), vc, vln, RAW(s_v, li, lj + 2));
+            if (by && ybuf(1, gj + 1, 2, NyG + 1)) vel[1] = sym2(vc, vln);
             vel[2] = vln;
             const double *const cu = &RAW(s_u, li, ln), *const cv = &RAW(s_v, li, ln), *const cA = &RAW(s_A, li, ln);
             double d1[3], d2[3], d3[3], d4[3], c0[3] = {es, es, es}, c1[3] = {es, es, es}, c2[3] = {es, es, es}, num[3], den[3], cc[3];
-            UPDC(vel[0] > 0.0, cu, W, 0, cc[0]); UPDC(vel[1] > 0.0, cv, W, 1, cc[1]); UPDC(vel[2] > 0.0, cA, W, 2, cc[2]);
+            UPDC(gt0(vel[0]), cu, W, 0, cc[0]); UPDC(gt0(vel[1]), cv, W, 1, cc[1]); UPDC(gt0(vel[2]), cA, W, 2, cc[2]);
             beta_acc_n<3>(d1, d2, d3, d4, c0, c1, c2);
-            corr_n<3>(d1, d2, d3, d4, c0, c1, c2, num, den);
+            corr10_n<3>(d1, d2, d3, d4, c0, c1, c2, num, den);
             // the three WENO denominators and the face depths ℑy h at cfc (li, ln), ℑxy h at ffc (li, ln): five reciprocals together
             double x5[5], rc[5];
             {
@@ -584,39 +605,37 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                 x5[3] = 0.5 * (h00 + h01);
                 x5[4] = avg4(RAW(s_h, li - 1, lj), h00, RAW(s_h, li - 1, ln), h01);
             }
-            rcp_n<5>(x5, rc);
+            rcp_mix_n<5, 3>(x5, rc);
             const double rhy_n = rc[3];
             rhff_n = rc[4];
             double fl[3];
 #pragma unroll
             for (int n = 0; n < 3; n++) fl[n] = vel[n] * fma(num[n], rc[n], cc[n]);
-            // Bounded-y wall buffers: centred second order (oracle ybuf)
-            if (ybuf(by, gj + 1, 3, NyG)) { fl[0] = vel[0] * sym2(cu[-W], cu[0]); fl[2] = vel[2] * sym2(cA[-W], cA[0]); }
-            if (ybuf(by, gj + 1, 3, NyG + 1)) fl[1] = vel[1] * sym2(cv[-W], cv[0]);
-            {   // F_vu - Lyx (advective_lorentz_flux_hBy_bx, :62-84 with its edge branches)
+            const double B0u = Bf(s_Bx, li, ln), Bmu = Bf(s_Bx, li, ln - 1);
+            const double L3u = third(B0u, Bmu, Bf(s_Bx, li, ln - 2)), R3u = thirdR(Bf(s_Bx, li, ln + 1), B0u, Bmu);
+            const double B0v = Bf(s_By, li, lj), Bpv = Bf(s_By, li, ln);
+            const double L3v = third(Bpv, B0v, Bf(s_By, li, lj - 1)), R3v = thirdR(Bf(s_By, li, lj + 2), Bpv, B0v);
+            double Lqu = L3u, Rqu = R3u, Lqv = L3v, Rqv = R3v;
+            if (by) {
+                // Bounded-y wall buffers: centred second order (oracle ybuf) and the edge branches of
+                // advective_lorentz_flux_hBy_bx / hBy_by (sw_mhd_divergence_functions.jl:62-84, 110-132)
+                if (ybuf(1, gj + 1, 3, NyG)) { fl[0] = vel[0] * sym2(cu[-W], cu[0]); fl[2] = vel[2] * sym2(cA[-W], cA[0]); }
+                if (ybuf(1, gj + 1, 3, NyG + 1)) fl[1] = vel[1] * sym2(cv[-W], cv[0]);
+                const int gjf = gj + 1;
+                if (gjf == 1) { Lqu = B0u; Rqu = B0u; } else if (gjf == 2) { Lqu = Bmu; Rqu = R3u; }
+                else if (gjf == NyG) { Lqu = L3u; Rqu = B0u; } else if (gjf == NyG + 1) { Lqu = Bmu; Rqu = Bmu; }
+                if (gj == 0) { Lqv = Bpv; Rqv = Bpv; } else if (gj == 1) { Lqv = B0v; Rqv = R3v; }
+                else if (gj == NyG - 1) { Lqv = L3v; Rqv = Bpv; } else if (gj == NyG) { Lqv = B0v; Rqv = B0v; }
+            }
+            {   // F_vu - Lyx (advective_lorentz_flux_hBy_bx, :62-84)
                 const double mom = (p.dx * fl[0]) * rhff_n;
                 const double vl = 0.5 * (Bf(s_hBy, li - 1, ln) + Bf(s_hBy, li, ln));
-                const double B0 = Bf(s_Bx, li, ln), Bm = Bf(s_Bx, li, ln - 1);
-                const double L3 = third(B0, Bm, Bf(s_Bx, li, ln - 2)), R3 = thirdR(Bf(s_Bx, li, ln + 1), B0, Bm);
-                double Lq = L3, Rq = R3;
-                if (by) {
-                    const int gjf = gj + 1;
-                    if (gjf == 1) { Lq = B0; Rq = B0; } else if (gjf == 2) { Lq = Bm; Rq = R3; }
-                    else if (gjf == NyG) { Lq = L3; Rq = B0; } else if (gjf == NyG + 1) { Lq = Bm; Rq = Bm; }
-                }
-                Fvu_n = p.dx * upwind_sel(vl, Lq, Rq) - mom;
+                Fvu_n = p.dx * upwind_sel(vl, Lqu, Rqu) - mom;
             }
             {   // F_vv - Lyy (advective_lorentz_flux_hBy_by, :110-132)
                 const double mom = (p.dx * fl[1]) * RH(li, lj);
                 const double vl = 0.5 * (Bf(s_hBy, li, lj) + Bf(s_hBy, li, ln));
-                const double B0 = Bf(s_By, li, lj), Bp = Bf(s_By, li, ln);
-                const double L3 = third(Bp, B0, Bf(s_By, li, lj - 1)), R3 = thirdR(Bf(s_By, li, lj + 2), Bp, B0);
-                double Lq = L3, Rq = R3;
-                if (by) {
-                    if (gj == 0) { Lq = Bp; Rq = Bp; } else if (gj == 1) { Lq = B0; Rq = R3; }
-                    else if (gj == NyG - 1) { Lq = L3; Rq = Bp; } else if (gj == NyG) { Lq = B0; Rq = B0; }
-                }
-                Fvv_c = p.dx * upwind_sel(vl, Lq, Rq) - mom;
+                Fvv_c = p.dx * upwind_sel(vl, Lqv, Rqv) - mom;
             }
             {   // tracer transport flux and vh/ℑy h at cfc (li, ln)
                 Ty_n = (p.dx * fl[2]) * rhy_n;
@@ -630,18 +649,16 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
             {
                 double vel[3];
                 vel[0] = sym4(RAW(s_u, li - 2, lj), RAW(s_u, li - 1, lj), uc, ue);
-                {
-                    const double u2 = sym2(us, uc), u4 = sym4(RAW(s_u, li, lj - 2), us, uc, RAW(s_u, li, lj + 1));
-                    vel[1] = ybuf(by, gj, 2, NyG) ? u2 : u4;
-                }
+                vel[1] = sym4(RAW(s_u, li, lj - 2), us, uc, RAW(s_u, li, lj + 1));
+                if (by && ybuf(1, gj, 2, NyG)) vel[1] = sym2(us, uc);
                 vel[2] = uc;
                 const double *const cu = &RAW(s_u, li, lj), *const cv = &RAW(s_v, li, lj), *const cA = &RAW(s_A, li, lj);
                 double d1[3], d2[3], d3[3], d4[3], c0[3] = {es, es, es}, c1[3] = {es, es, es}, c2[3] = {es, es, es}, num[3], den[3], cc[3];
-                UPDC(vel[0] > 0.0, cu, 1, 0, cc[0]); UPDC(vel[1] > 0.0, cv, 1, 1, cc[1]); UPDC(vel[2] > 0.0, cA, 1, 2, cc[2]);
+                UPDC(gt0(vel[0]), cu, 1, 0, cc[0]); UPDC(gt0(vel[1]), cv, 1, 1, cc[1]); UPDC(gt0(vel[2]), cA, 1, 2, cc[2]);
                 beta_acc_n<3>(d1, d2, d3, d4, c0, c1, c2);
-                corr_n<3>(d1, d2, d3, d4, c0, c1, c2, num, den);
+                corr10_n<3>(d1, d2, d3, d4, c0, c1, c2, num, den);
                 double x4[4] = {den[0], den[1], den[2], 0.5 * (RAW(s_h, li - 1, lj) + RAW(s_h, li, lj))}, rc[4];   // + ℑx h at fcc (li, lj)
-                rcp_n<4>(x4, rc);
+                rcp_mix_n<4, 3>(x4, rc);
                 double fl[3];
 #pragma unroll
                 for (int n = 0; n < 3; n++) fl[n] = vel[n] * fma(num[n], rc[n], cc[n]);
@@ -674,6 +691,7 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
             const double hc = RAW(s_h, li, lj), hw_ = RAW(s_h, li - 1, lj), hs = RAW(s_h, li, lj - 1);
             const double Pc = __dmul_rn(hg, __dmul_rn(hc, hc)), Pw = __dmul_rn(hg, __dmul_rn(hw_, hw_)), Ps = __dmul_rn(hg, __dmul_rn(hs, hs));
             const double vc = RAW(s_v, li, lj), vn = RAW(s_v, li, ln);
+            const double Ac = RAW(s_A, li, lj);
             double Gn0, Gn1 = 0.0, Gn2, Gn3;
             {   // Guh (dm holds div(Lorentz - momentum flux))
                 const double dm = p.inv_az * ((Fuu_e - Fuu_w) + (Fvu_n - Fvu_s));
@@ -690,30 +708,41 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
             {   // Gh (centred), GA
                 Gn2 = -fma(ue - uc, p.rdx, (vn - vc) * p.rdy);
                 const double d = p.inv_az * ((Tx_e - Tx_w) + (Ty_n - Ty_s));
-                const double cdiv = (uq_e - uq_w) * p.rdx + (vq_n - vq_s) * p.rdy;
-                Gn3 = -d + RAW(s_A, li, lj) * cdiv;
+                const double cdiv = fma(uq_e - uq_w, p.rdx, (vq_n - vq_s) * p.rdy);
+                Gn3 = fma(Ac, cdiv, -d);
             }
             if (active) {
                 const double Gn[4] = {Gn0, Gn1, Gn2, Gn3};
-                const double Gm[4] = {Gm0, Gm1, Gm2, Gm3};
-                const double Uc[4] = {uc, vc, hc, RAW(s_A, li, lj)};
+                const double Gm[4] = {Gq0, Gq1, Gq2, Gq3};
+                const double Uc[4] = {uc, vc, hc, Ac};
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                     if constexpr (STAGE == 1) {
-                        p.Un[k][gcell] = Uc[k] + p.dtgam * Gn[k];
+                        p.Un[k][gcell] = fma(p.dtgam, Gn[k], Uc[k]);
                         p.G[k][gcell] = Gn[k];
                     } else {
-                        p.Un[k][gcell] = Uc[k] + p.dt * (p.gam * Gn[k] + p.zet * Gm[k]);
+                        p.Un[k][gcell] = fma(p.dtgam, Gn[k], fma(p.dtzet, Gm[k], Uc[k]));
                         if constexpr (STAGE == 2) p.G[k][gcell] = Gn[k];
                     }
                 }
             }
+            if constexpr (STAGE >= 2) {     // G^- of the next row: requested now, consumed at the end of the next iteration
+                if (it + 1 < R && own && (j + 1 <= p.row_end)) {
+                    const size_t gn = gcell + (size_t)P;
+                    Gq0 = p.G[0][gn]; Gq1 = p.G[1][gn]; Gq2 = p.G[2][gn]; Gq3 = p.G[3][gn];
+                }
+            }
         }
         Fvu_s = Fvu_n; Fvv_s = Fvv_c; Ty_s = Ty_n; vq_s = vq_n; rhff_s = rhff_n;
+        gcell += (size_t)P;
     }
 
     // ---- fused diagnostics of the state at the start of the step ------------------------------
     if constexpr (DIAG) {
+        double dg[NDIAG];
+#pragma unroll
+        for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
+        dg[6] = -INFINITY;
         double *const s_red = smem + DERIVED_D + 2;
         constexpr int NR = R + 2;                            // rows b = lj0-1 .. lj0+R, index k = b - (lj0-1)
         auto sq = [](double x) { return x * x; };

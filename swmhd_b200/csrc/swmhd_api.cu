@@ -482,6 +482,7 @@ static KParams kparams(swmhd_ctx *ctx, const Slab &s, double dt, int stage) {
     p.zet = stage >= 1 ? RK_ZETA[stage - 1] : 0.0;
     p.dtgam = dt * p.gam;
     p.dtzet = dt * p.zet;
+    p.qrdxy = 0.25 * p.rdx * p.rdy;
     for (int k = 0; k < 4; k++) {
         p.Uo[k] = s.U[ctx->cur][k];
         p.Un[k] = s.U[1 - ctx->cur][k];

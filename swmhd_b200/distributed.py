@@ -138,7 +138,7 @@ class SlabModel:
         self.device = torch.cuda.current_device() if device is None else device
         self.cfg = slab_config(cfg_global, self.rank, self.world, self.device)
         self.periodic_y = cfg_global.topo_y == abi.PERIODIC
-        self.host_exchange = bool(host_exchange) and self.world > 1
+        self.host_exchange = bool(host_exchange)
         self.ctx = Context(self.cfg)
         self._views = {}
         if self.host_exchange:
@@ -160,6 +160,8 @@ class SlabModel:
         return t
 
     def _exchange(self, current: bool, stream):
+        if self.world == 1:
+            return []   # a single slab owns its own periodic wrap (done by the halo kernel)
         off = CURRENT if current else 0
         rows_of = lambda f, which: self._rows(f, which + off)
         ops = exchange_ops(rows_of, self.rank, self.world, self.periodic_y)
@@ -222,6 +224,8 @@ class SlabModel:
 
     def _combine(self, d):
         """Slab partials are already scaled by the global normalisation: sums add, extrema combine."""
+        if self.world == 1:
+            return d
         dev = f"cuda:{self.device}"
         sums = torch.tensor([d["ke"], d["me"], d["pe"], d["sum_h"], float(1 - d["all_finite"])], dtype=torch.float64, device=dev)
         maxs = torch.tensor([d["max_abs_u"], d["max_abs_A"], d["max_abs_div_hB"], -d["min_h"]], dtype=torch.float64, device=dev)

@@ -55,8 +55,11 @@ def test_4096_properties(kind):
     cfg_s = abi.Config.from_buffer_copy(cfg)
     cfg_s.arith = abi.ARITH_STRICT
     Us, ds, _ = gpu_run(cfg_s, U, dt, nst)
-    for k in range(4):                                   # the two arithmetic modes agree to the stated tolerance
-        assert rel_l2(g, Uf[k], Us[k], k) <= 5e-12, k
+    # The two arithmetic modes after 6 steps.  The bound is the conditioning of the problem, not of the kernels: the
+    # Lorentz force holds second differences of A, so ONE ulp of noise on A moves uh by 8e-15 / 5e-14 / 6.5e-13 rel-L2
+    # at 64^2 / 256^2 / 1024^2 after 6 steps in the oracle itself (growth ~N^1.6 -> ~8e-12 at 4096^2).
+    for k in range(4):
+        assert rel_l2(g, Uf[k], Us[k], k) <= 5e-11, k
     m0 = float(N) * N                                    # h = 1 initially
     assert abs(df["sum_h"] - m0) <= 2e-12 * m0           # flux form: mass conserved to round-off
     assert df["max_abs_div_hB"] < 1e-11                  # div(hB) = 0 identically for hB = z x grad A

@@ -40,6 +40,8 @@ def test_strict_bit_identical_one_step(kind, N):
 @pytest.mark.parametrize("kind", ["J", "D", "G", "GD"])
 @pytest.mark.parametrize("N", [64, 100])
 def test_fast_one_step_tolerance(kind, N):
+    # J, G perturbed; D, GD as the script sets them (uh = vh = 0: the tight case of SURVEY B.6); the perturbed
+    # divergence cases are test_fast_one_step_perturbed_divergence (tests/test_gpu_round2.py)
     g, cfg, U = make_case(kind, N, arith=abi.ARITH_FAST, perturb=7 if kind in ("J", "G") else None)
     Ug = run_gpu(cfg, U, 0.01 * 64 / N, 1)
     O.fill_halos(cfg, U)
@@ -135,7 +137,12 @@ def test_fused_step_diagnostics(kind, arith):
         for key in ("ke", "me", "pe", "total", "sum_h"):
             assert abs(dg[n][key] - do[key]) <= 2e-13 * max(1.0, abs(do[key])), (n, key, dg[n][key], do[key])
         for key in ("max_abs_A", "min_h"):
-            assert dg[n][key] == do[key], (n, key)
+            # extrema are exact reductions of the state: equal whenever the states are (always for STRICT and for
+            # the initial state; a FAST state differs from the oracle's by ulps from the first step on)
+            if arith == abi.ARITH_STRICT or n == 0:
+                assert dg[n][key] == do[key], (n, key)
+            else:
+                assert abs(dg[n][key] - do[key]) <= 1e-14 * abs(do[key]), (n, key)
         assert abs(dg[n]["max_abs_u"] - do["max_abs_u"]) <= 1e-15 * max(1.0, do["max_abs_u"])
         assert abs(dg[n]["max_abs_div_hB"] - do["max_abs_div_hB"]) < 1e-13
         O.step(cfg, U, 0.004, 1)
@@ -161,7 +168,7 @@ def test_slab_api_single_rank_equals_step(kind):
     from swmhd_b200.distributed import SlabModel
     g, cfg, U = make_case(kind, 96, Ny=80, arith=abi.ARITH_FAST, perturb=17)
     a = run_gpu(cfg, U, 0.004, 3)
-    sm = SlabModel(cfg, rank=0, world=1, device=0)
+    sm = SlabModel(cfg, rank=0, world=1, device=0, host_exchange=True)
     sm.set_state(U)
     sm.fill_halos()
     tr = sm.step_diag(0.004, 3)
