@@ -284,8 +284,9 @@ class Leg:
         """W warm-up steps, then K steps (diagnostics every step, fused into stage 1) between CUDA events on
         the launching stream (inside swmhd_step_diag), barrier + synchronize on both sides, max over ranks."""
         env = self.env
-        if sampler:
+        if sampler:                 # rank 0 only
             sampler.start()
+        if busy > 0:                # EVERY rank: a slab step exchanges halo rows with its neighbours
             self.keep_busy(busy)
             self.reset()
         self.m.step_diag(self.dt, max(W, 1))

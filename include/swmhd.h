@@ -80,7 +80,10 @@ enum {
     SWMHD_FLAG_BC_DEPTH1      = 1 << 4, /* no-flux / gradient BCs fill only the first halo row */
     SWMHD_FLAG_WALL_WENO3     = 1 << 5, /* one cell further from the wall than the centred
                                            fallback needs: WENO3 instead of centred 2nd order  */
-    SWMHD_FLAG_V_MIRROR       = 1 << 6  /* v|vh beyond the wall: odd mirror instead of untouched */
+    SWMHD_FLAG_V_MIRROR       = 1 << 6, /* v|vh beyond the wall: odd mirror instead of untouched */
+    /* not in the register: what ELSE could explain the 64^2 Bounded-y deviation (same probe) */
+    SWMHD_FLAG_TRACER_CEN2    = 1 << 7, /* A advected with centred 2nd order instead of WENO5     */
+    SWMHD_FLAG_TRACER_CEN4    = 1 << 8  /* A advected with centred 4th order instead of WENO5     */
 };
 
 typedef struct swmhd_config {

@@ -389,12 +389,30 @@ static double Gv_vi(const S *s, int i, int j) { /* cfc */
     return (((-adv - dK) - pg) - s->f * uhat) + lorentz_force_func_y(s, i, j);
 }
 /* advective flux of centre-located c by (u,v): fcc and cfc */
+/* probe only: the tracer A reconstructed with a centred interpolant (both upwind sides equal) */
+static inline int tracer_centred(const S *s, fn2 C) {
+    return C == fA && (s->flags & (SWMHD_FLAG_TRACER_CEN2 | SWMHD_FLAG_TRACER_CEN4));
+}
+static inline void rec_x(const S *s, fn2 C, int i, int j, double *L, double *R) {
+    if (tracer_centred(s, C)) {
+        *L = *R = (s->flags & SWMHD_FLAG_TRACER_CEN2) ? sym2(C(s, i - 1, j), C(s, i, j)) : sym_x(s, C, i, j);
+        return;
+    }
+    weno_x(s, C, i, j, L, R);
+}
+static inline void rec_y(const S *s, fn2 C, int i, int j, double *L, double *R) {
+    if (tracer_centred(s, C)) {
+        *L = *R = (s->flags & SWMHD_FLAG_TRACER_CEN2) ? sym2(C(s, i, j - 1), C(s, i, j)) : sym_y(s, C, i, j, YC_HI(s));
+        return;
+    }
+    weno_y(s, C, i, j, YC_HI(s), L, R);
+}
 static inline double adv_flux_x(const S *s, fn2 C, int i, int j) {
-    double L, R; weno_x(s, C, i, j, &L, &R);
+    double L, R; rec_x(s, C, i, j, &L, &R);
     return s->dy * upwind(fU(s, i, j), L, R);
 }
 static inline double adv_flux_y(const S *s, fn2 C, int i, int j) {
-    double L, R; weno_y(s, C, i, j, YC_HI(s), &L, &R);
+    double L, R; rec_y(s, C, i, j, &L, &R);
     return s->dx * upwind(fV(s, i, j), L, R);
 }
 static inline double div_xy(const S *s, int i, int j) { /* div_xyᶜᶜᶜ(u|uh, v|vh) */
@@ -455,11 +473,11 @@ static double Gvh_c(const S *s, int i, int j) { /* cfc */
 }
 static double Gh_c(const S *s, int i, int j) { return -div_xy(s, i, j); } /* centred (C7) */
 static inline double tr_flux_x(const S *s, int i, int j) { /* transport tracer flux / ℑxᶠ h */
-    double L, R; weno_x(s, fA, i, j, &L, &R);
+    double L, R; rec_x(s, fA, i, j, &L, &R);
     return s->dy * upwind(fU(s, i, j), L, R) / ixf_h(s, i, j);
 }
 static inline double tr_flux_y(const S *s, int i, int j) {
-    double L, R; weno_y(s, fA, i, j, YC_HI(s), &L, &R);
+    double L, R; rec_y(s, fA, i, j, &L, &R);
     return s->dx * upwind(fV(s, i, j), L, R) / iyf_h(s, i, j);
 }
 static inline double u_of(const S *s, int i, int j) { return fU(s, i, j) / ixf_h(s, i, j); } /* uh/ℑxᶠh */

@@ -20,6 +20,7 @@ U, V, H, A = 0, 1, 2, 3
 ARITH_FAST, ARITH_STRICT = 0, 1
 FLAG_WENO_JS, FLAG_PRESSURE_GHDH, FLAG_CDIVU_OVER_H, FLAG_DIAG_CENTRED = 1, 2, 4, 8
 FLAG_BC_DEPTH1, FLAG_WALL_WENO3, FLAG_V_MIRROR = 16, 32, 64      # C10 probe (oracle only)
+FLAG_TRACER_CEN2, FLAG_TRACER_CEN4 = 128, 256                     # same probe: centred tracer advection
 HALO = 3
 
 

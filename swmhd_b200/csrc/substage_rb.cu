@@ -57,7 +57,11 @@ constexpr int CP = TX + 2, CR = TYB + 2;                   // ccc points a in [2
 constexpr int NZ = ZP * ZR, NC = CP * CR;
 constexpr int o_z = 0, o_ut = NZ, o_vt = 2 * NZ, o_Bx = 3 * NZ, o_By = o_Bx + NC;
 constexpr int DERIVED = o_By + NC;
-constexpr size_t SMEM_BYTES = ((size_t)4 * SZP + DERIVED + 2 + NW * NDIAG) * sizeof(double);   // + mbarrier + DIAG partials
+// per warp: the tile's east column of faces, read by lane 31 only: R h fluxes, R A fluxes; DIAG variant: R+2 squared
+// By values and R kinetic-energy brackets.  The warp's DIAG partials (NDIAG doubles) reuse its slice at the end.
+constexpr int NE = 4 * R + 2;
+static_assert(NE >= NDIAG, "the per-warp scratch also holds the warp's diagnostic partials");
+constexpr size_t SMEM_BYTES = ((size_t)4 * SZP + DERIVED + 2 + NW * NE) * sizeof(double);   // + mbarrier + per-warp scratch
 
 #define RAW(arr, a, b) arr[(b) * W + (a)]
 #define Zf(arr, a, b) arr[((b) - 1) * ZP + (a) - 1]
@@ -180,12 +184,29 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     // warps of a ragged last tile row (or of an 8-row edge strip) that own no cell skip the row walk
     const bool warp_has_rows = (jc0 <= p.row_end);
 
-    // B0: the tile's east column of x faces for this warp's rows: lanes 0..R-1 take h, lanes R..2R-1 take A
-    double eastF = 0.0;
-    if (warp_has_rows && lane < 2 * R) {
-        const int b = lj0 + (lane & (R - 1));
-        const double *arr = (lane < R) ? s_h : s_A;
-        eastF = upwind_weno_mem(&RAW(arr, TX + 3, b), RAW(s_u, TX + 3, b), eps);
+    // B0: the tile's east column (a = TX+3) for this warp's rows, into the warp's scratch slice (lane 31 reads it in
+    // the row walk): lanes 0..R-1 the h fluxes, lanes R..2R-1 the A fluxes; DIAG: lanes 2R..3R+1 the squared By of
+    // rows lj0-1..lj0+R, lanes 3R+2..4R+1 the kinetic-energy brackets of rows lj0..lj0+R-1
+    double *const s_e = smem + DERIVED + 2 + wp * NE;
+    if (warp_has_rows) {
+        constexpr int a = TX + 3;
+        if (lane < 2 * R) {
+            const int b = lj0 + (lane & (R - 1));
+            const double *arr = (lane < R) ? s_h : s_A;
+            s_e[lane] = upwind_weno_mem(&RAW(arr, a, b), RAW(s_u, a, b), eps);
+        }
+        if constexpr (DIAG) {
+            if (lane >= 2 * R && lane < 3 * R + 2) {
+                const int b = lj0 - 1 + (lane - 2 * R);
+                const double by_ = ((RAW(s_A, a, b) - RAW(s_A, a - 1, b)) * p.rdx) * frcp(0.5 * (RAW(s_h, a - 1, b) + RAW(s_h, a, b)));
+                s_e[lane] = by_ * by_;
+            } else if (lane >= 3 * R + 2 && lane < 4 * R + 2) {
+                const int b = lj0 + (lane - (3 * R + 2));
+                const double v00 = RAW(s_v, a - 1, b), v10 = RAW(s_v, a, b), v01 = RAW(s_v, a - 1, b + 1), v11 = RAW(s_v, a, b + 1), ua = RAW(s_u, a, b);
+                s_e[lane] = fma(ua, ua, avg4(v00 * v00, v10 * v10, v01 * v01, v11 * v11));
+            }
+        }
+        __syncwarp();
     }
 
     // Row loop.  Iteration it = -1 only produces the fluxes through the south face of the warp's first
@@ -194,6 +215,10 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     double fyh_s = 0.0, fyA_s = 0.0, K_s = 0.0;
     const double es1 = eps * (12.0 / 13.0), es2 = eps * (24.0 / 13.0);
     const bool col_ok = (i <= Nx);
+    // DIAG: energy sums accumulated in the row walk (they need the reciprocal face depths it holds anyway);
+    // sqy_s = By^2 at fcc (li, lj-1), meb_s = ME bracket at cfc (li, lj-1): one row behind
+    double ke_acc = 0.0, me_acc = 0.0, sqy_s = 0.0, meb_s = 0.0;
+    (void)ke_acc; (void)me_acc; (void)sqy_s; (void)meb_s;
     size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(jc0 + 1);   // cell (i, jc0 - 1): advanced by one row per iteration
 
 #pragma unroll 1
@@ -216,7 +241,15 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
             UPDC(posN, ph, W, 0, ch); UPDC(posN, pA, W, 1, cA);
             beta_acc_n<2>(d1, d2, d3, d4, c0, c1, c2);
             corr10_n<2>(d1, d2, d3, d4, c0, c1, c2, num, den);
-            rcp_mix_n<2, 2>(den, rc);
+            if constexpr (DIAG) {   // By^2 at fcc (li, lj0-1) seeds the magnetic-energy bracket of the first row
+                double x3[3] = {den[0], den[1], 0.5 * (RAW(s_h, li - 1, lj) + ph[-W])}, r3[3];
+                rcp_mix_n<3, 2>(x3, r3);
+                rc[0] = r3[0]; rc[1] = r3[1];
+                const double by_ = ((pA[-W] - RAW(s_A, li - 1, lj)) * p.rdx) * r3[2];
+                sqy_s = by_ * by_;
+            } else {
+                rcp_mix_n<2, 2>(den, rc);
+            }
             fyh_n = vN * fma(num[0], rc[0], ch);
             fyA_n = vN * fma(num[1], rc[1], cA);
         } else {
@@ -267,8 +300,7 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
             const double adv_v = uhat * fma(num2[1], rc[1], cz1);
             // east faces: the neighbour lane's west face; lane 31 takes the pre-pass value
             double fxh_e = __shfl_down_sync(0xffffffffu, fxh, 1), fxA_e = __shfl_down_sync(0xffffffffu, fxA, 1);
-            const double eh = __shfl_sync(0xffffffffu, eastF, it), eA = __shfl_sync(0xffffffffu, eastF, R + it);
-            if (lane == 31) { fxh_e = eh; fxA_e = eA; }
+            if (lane == 31) { fxh_e = s_e[it]; fxA_e = s_e[R + it]; }
 
             double Gn0, Gn1, Gn2, Gn3;
             const double Ac = pA[-W], An = pA[0], As = RAW(s_A, li, lj - 1);
@@ -317,6 +349,21 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
                     }
                 }
             }
+            if constexpr (DIAG) {
+                // KE bracket u^2 + ℑxyᶠᶜᵃ(v^2) at fcc (li, lj); ME bracket Bx^2 + ℑxyᶜᶠᵃ(By^2) at cfc (li, lj) with
+                // Bx = -dyA / ℑy h at cfc, By = dxA / ℑx h at fcc (SWMHD_example.jl:70-75); the east
+                // neighbours come from lane+1, lane 31 takes the tile's east column from the warp's scratch slice
+                const double byf = ((Ac - Aw) * p.rdx) * rc[6], bxf = ((Ac - As) * p.rdy) * rc[7];
+                const double sqy = byf * byf;
+                const double csum = sqy_s + sqy;
+                const double keb = fma(uw, uw, avg4(vW * vW, vC * vC, vWn * vWn, vN * vN));
+                double csum_e = __shfl_down_sync(0xffffffffu, csum, 1), keb_e = __shfl_down_sync(0xffffffffu, keb, 1);
+                if (lane == 31) { csum_e = s_e[2 * R + it] + s_e[2 * R + it + 1]; keb_e = s_e[3 * R + 2 + it]; }
+                const double meb = fma(0.25, csum + csum_e, bxf * bxf);
+                if (it >= 1 && col_ok && (j - 1 <= p.row_end)) me_acc = fma(0.25 * hs, meb_s + meb, me_acc);   // cell (li, lj-1): (h/2) (meb_s + meb)/2
+                if (active) ke_acc = fma(0.25 * hc, keb + keb_e, ke_acc);               // cell (li, lj):   (h/2) (keb + keb_e)/2
+                meb_s = meb; sqy_s = sqy;
+            }
             // G^- of the next row: requested now, consumed at the end of the next iteration (the first row's was
             // requested before the tile wait)
             if constexpr (STAGE >= 2) {
@@ -335,125 +382,75 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     }
 
     // ---- fused diagnostics of the state at the start of the step --------------------------
-    // Warp-private like the rest: every thread evaluates the squared face fields of its own column for
-    // its R cells from the raw tile (2R+3 reciprocals advanced together), the east neighbours come by
-    // shuffle, the tile's east column from lanes 0..R+1.
+    // KE and ME were accumulated in the row walk.  Left: the magnetic-energy bracket north of the warp's last row
+    // (two more reciprocal depths), and the quantities that need no reciprocal (PE, mass, extrema, div(hB), finite
+    // flag), evaluated per thread for its R cells from the raw tile.
     if constexpr (DIAG) {
         double dg[NDIAG];
 #pragma unroll
         for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
         dg[6] = -INFINITY;
-        double *const s_red = smem + DERIVED + 2;            // NW x NDIAG partials (behind the mbarrier word)
-        constexpr int NR = R + 2;                            // rows b = lj0-1 .. lj0+R, index k = b - (lj0-1)
-        auto sq = [](double x) { return x * x; };
-        double Ac[NR], Aw[NR], Ae[NR], hcol[NR], sqy[NR], sqx[NR];
-        {
-            double den[2 * NR - 1], rc[2 * NR - 1], hwst[NR];
-#pragma unroll
-            for (int k = 0; k < NR; k++) {
-                const int b = lj0 - 1 + k;
-                Ac[k] = RAW(s_A, li, b); Aw[k] = RAW(s_A, li - 1, b); Ae[k] = RAW(s_A, li + 1, b);
-                hcol[k] = RAW(s_h, li, b); hwst[k] = RAW(s_h, li - 1, b);
+        if (warp_has_rows) {
+            {   // ME of the cell (li, lj0+R-1): bracket at cfc (li, lj0+R)
+                const int lt = lj0 + R;
+                const double hN = RAW(s_h, li, lt), hC = RAW(s_h, li, lt - 1), AN = RAW(s_A, li, lt);
+                double x2[2] = {0.5 * (RAW(s_h, li - 1, lt) + hN), 0.5 * (hC + hN)}, r2[2];
+                rcp_n<2>(x2, r2);
+                const double byf = ((AN - RAW(s_A, li - 1, lt)) * p.rdx) * r2[0], bxf = ((AN - RAW(s_A, li, lt - 1)) * p.rdy) * r2[1];
+                const double csum = fma(byf, byf, sqy_s);
+                double csum_e = __shfl_down_sync(0xffffffffu, csum, 1);
+                if (lane == 31) csum_e = s_e[3 * R] + s_e[3 * R + 1];
+                const double meb = fma(0.25, csum + csum_e, bxf * bxf);
+                if (col_ok && (jc0 + R - 1 <= p.row_end)) me_acc = fma(0.25 * hC, meb_s + meb, me_acc);
             }
+            dg[0] = ke_acc; dg[1] = me_acc;
+            double Am[3], A0[3], Ap[3];                      // A at columns li-1, li, li+1 of rows lj-1, lj, lj+1 (sliding)
 #pragma unroll
-            for (int k = 0; k < NR; k++) den[k] = 0.5 * (hwst[k] + hcol[k]);                 // ℑx h at fcc(li, b)
+            for (int c = 0; c < 3; c++) { Am[c] = RAW(s_A, li - 1 + c, lj0 - 1); A0[c] = RAW(s_A, li - 1 + c, lj0); }
 #pragma unroll
-            for (int k = 1; k < NR; k++) den[NR + k - 1] = 0.5 * (hcol[k - 1] + hcol[k]);     // ℑy h at cfc(li, b)
-            {   // two batches: eleven reciprocals in flight at once do not fit the register budget of 4 CTAs per SM
-                double xa[NR], ra[NR], xb[NR - 1], rb[NR - 1];
+            for (int r = 0; r < R; r++) {
+                const int lj = lj0 + r;
 #pragma unroll
-                for (int k = 0; k < NR; k++) xa[k] = den[k];
-                rcp_n<NR>(xa, ra);
-#pragma unroll
-                for (int k = 0; k < NR; k++) rc[k] = ra[k];
-#pragma unroll
-                for (int k = 0; k < NR - 1; k++) xb[k] = den[NR + k];
-                rcp_n<NR - 1>(xb, rb);
-#pragma unroll
-                for (int k = 0; k < NR - 1; k++) rc[NR + k] = rb[k];
-            }
-#pragma unroll
-            for (int k = 0; k < NR; k++) sqy[k] = sq(((Ac[k] - Aw[k]) * p.rdx) * rc[k]);      // (dxA / ℑx h)^2
-            sqx[0] = 0.0;
-#pragma unroll
-            for (int k = 1; k < NR; k++) sqx[k] = sq(-((Ac[k] - Ac[k - 1]) * p.rdy) * rc[NR + k - 1]);   // (dyA / ℑy h)^2
-        }
-        double uu[R], vc[R + 1], kb[R];
-        {
-            double vw2[R + 1], vc2[R + 1];
-#pragma unroll
-            for (int k = 0; k <= R; k++) { vc[k] = RAW(s_v, li, lj0 + k); vc2[k] = sq(vc[k]); vw2[k] = sq(RAW(s_v, li - 1, lj0 + k)); }
-#pragma unroll
-            for (int r = 0; r < R; r++) {                    // KE bracket u^2 + ℑxyᶠᶜᵃ(v^2) at fcc(li)
-                uu[r] = RAW(s_u, li, lj0 + r);
-                kb[r] = sq(uu[r]) + avg4(vw2[r], vc2[r], vw2[r + 1], vc2[r + 1]);
-            }
-        }
-        // the tile's east column (a = TX+3), lane l takes row k = l
-        double e_sqy = 0.0, e_kb = 0.0;
-        if (lane < NR) {
-            const int b = lj0 - 1 + lane, a = TX + 3;
-            e_sqy = sq(((RAW(s_A, a, b) - RAW(s_A, a - 1, b)) * p.rdx) * frcp(0.5 * (RAW(s_h, a - 1, b) + RAW(s_h, a, b))));
-            if (lane < R) {
-                const int bb = lj0 + lane;
-                e_kb = sq(RAW(s_u, a, bb)) + avg4(sq(RAW(s_v, a - 1, bb)), sq(RAW(s_v, a, bb)), sq(RAW(s_v, a - 1, bb + 1)), sq(RAW(s_v, a, bb + 1)));
-            }
-        }
-        double sqye[NR], kbe[R];
-#pragma unroll
-        for (int k = 0; k < NR; k++) {
-            sqye[k] = __shfl_down_sync(0xffffffffu, sqy[k], 1);
-            const double t = __shfl_sync(0xffffffffu, e_sqy, k);
-            if (lane == 31) sqye[k] = t;
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            kbe[r] = __shfl_down_sync(0xffffffffu, kb[r], 1);
-            const double t = __shfl_sync(0xffffffffu, e_kb, r);
-            if (lane == 31) kbe[r] = t;
-        }
-        double mb[R + 1];                                    // ME bracket Bx^2 + ℑxyᶜᶠᵃ(By^2) at cfc(li, b), b = lj0 .. lj0+R
-#pragma unroll
-        for (int k = 1; k < NR; k++) mb[k - 1] = sqx[k] + avg4(sqy[k - 1], sqye[k - 1], sqy[k], sqye[k]);
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int j = jc0 + r, k = r + 1;
-            if ((i <= Nx) && (j <= p.row_end)) {
-                const double hh = hcol[k], aa = Ac[k];
-                dg[0] += (0.5 * hh) * (0.5 * (kb[r] + kbe[r]));
-                dg[1] += (0.5 * hh) * (0.5 * (mb[r] + mb[r + 1]));
-                const double dh = hh - p.h_ref;
-                dg[2] += (0.5 * p.g) * (dh * dh);
-                dg[3] += hh;
-                dg[4] = fmax(dg[4], fabs(uu[r]));
-                dg[5] = fmax(dg[5], fabs(aa));
-                dg[6] = fmax(dg[6], -hh);
-                {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
-                    const double hbx0 = (Aw[k - 1] + Ac[k - 1]) - (Aw[k + 1] + Ac[k + 1]), hbx1 = (Ac[k - 1] + Ae[k - 1]) - (Ac[k + 1] + Ae[k + 1]);
-                    const double hby0 = (Ae[k - 1] + Ae[k]) - (Aw[k - 1] + Aw[k]), hby1 = (Ae[k] + Ae[k + 1]) - (Aw[k] + Aw[k + 1]);
-                    dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
+                for (int c = 0; c < 3; c++) Ap[c] = RAW(s_A, li - 1 + c, lj + 1);
+                if (col_ok && (jc0 + r <= p.row_end)) {
+                    const double hh = RAW(s_h, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj), aa = A0[1];
+                    const double dh = hh - p.h_ref;
+                    dg[2] = fma(0.5 * p.g, dh * dh, dg[2]);
+                    dg[3] += hh;
+                    dg[4] = fmax(dg[4], fabs(uu));
+                    dg[5] = fmax(dg[5], fabs(aa));
+                    dg[6] = fmax(dg[6], -hh);
+                    {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
+                        const double hbx0 = (Am[0] + Am[1]) - (Ap[0] + Ap[1]), hbx1 = (Am[1] + Am[2]) - (Ap[1] + Ap[2]);
+                        const double hby0 = (Am[2] + A0[2]) - (Am[0] + A0[0]), hby1 = (A0[2] + Ap[2]) - (A0[0] + Ap[0]);
+                        dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
+                    }
+                    if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) dg[8] += 1.0;
                 }
-                if (!(isfinite(hh) && isfinite(aa) && isfinite(uu[r]) && isfinite(vc[r]))) dg[8] += 1.0;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { Am[c] = A0[c]; A0[c] = Ap[c]; }
             }
         }
         // fixed-order reduction: R cells per thread (above), warp tree, then the warps in order
+        double *const s_red = smem + DERIVED + 2;            // warp w's partials at the start of its scratch slice
+        __syncwarp();                                        // lane 31 has read the last east-column values
 #pragma unroll
         for (int q = 0; q < NDIAG; q++) {
             const bool is_max = (q >= 4 && q <= 7);
             const double x = is_max ? warp_max(dg[q]) : warp_sum(dg[q]);
-            if (lane == 0) s_red[wp * NDIAG + q] = x;
+            if (lane == 0) s_red[wp * NE + q] = x;
         }
         __syncthreads();
         if (tid < NDIAG) {
             const bool is_max = (tid >= 4 && tid <= 7);
             double acc = s_red[tid];
-            for (int w2 = 1; w2 < NW; w2++) { const double x = s_red[w2 * NDIAG + tid]; acc = is_max ? fmax(acc, x) : acc + x; }
+            for (int w2 = 1; w2 < NW; w2++) { const double x = s_red[w2 * NE + tid]; acc = is_max ? fmax(acc, x) : acc + x; }
             // partial slots are indexed by 8-row tile rows (the launch granularity of the host side): this
             // tile fills its first slot and neutral elements into the others it covers
             const int tr8 = row0 / 8;
             p.diag[((size_t)tr8 * tiles_x + tile_x) * NDIAG + tid] = acc;
-            for (int s = 1; s < TYB / 8; s++)
-                if (row0 + 8 * s < p.row_end) p.diag[((size_t)(tr8 + s) * tiles_x + tile_x) * NDIAG + tid] = (tid == 6) ? -INFINITY : 0.0;
+            for (int s2 = 1; s2 < TYB / 8; s2++)
+                if (row0 + 8 * s2 < p.row_end) p.diag[((size_t)(tr8 + s2) * tiles_x + tile_x) * NDIAG + tid] = (tid == 6) ? -INFINITY : 0.0;
         }
     }
 }
@@ -576,6 +573,11 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
     double rhff_s = 0.0;                                       // 1/ℑxy h at the ffc point (li, lj), likewise
     const bool warp_has_rows = (jc0 <= p.row_end);             // ragged last tile row / 8-row edge strips
     size_t gcell = (size_t)(i + 2) + (size_t)P * (size_t)(jc0 + 1);   // cell (i, jc0 - 1): one row further per iteration
+    // DIAG: the sums and the maximum that need reciprocal face depths are accumulated in the row walk, which holds them
+    // anyway.  sqx_s = Bx^2 at cfc (li, lj) (from the previous iteration's north side), sqy_s = By^2 at fcc (li, lj-1),
+    // meb_s = ME bracket at cfc (li, lj-1).
+    double ke_acc = 0.0, me_acc = 0.0, mu_acc = 0.0, sqx_s = 0.0, sqy_s = 0.0, meb_s = 0.0;
+    (void)ke_acc; (void)me_acc; (void)mu_acc; (void)sqx_s; (void)sqy_s; (void)meb_s;
 
 #pragma unroll 1
     for (int it = warp_has_rows ? -1 : R; it < R; ++it) {
@@ -583,7 +585,8 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
         const int j = jc0 + it, gj = gj0 + it;
         const bool active = own && (j <= p.row_end);
         // ---- north side: F_vu - Lyx at ffc (li, ln), F_vv - Lyy at ccc (li, lj), tracer flux at cfc (li, ln) ----
-        double Fvu_n, Fvv_c, Ty_n, vq_n, rhff_n;
+        double Fvu_n, Fvv_c, Ty_n, vq_n, rhff_n, sqx_n = 0.0;
+        (void)sqx_n;
         {
             const double vln = RAW(s_v, li, ln);
             double vel[3];
@@ -641,11 +644,19 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                 Ty_n = (p.dx * fl[2]) * rhy_n;
                 vq_n = vln * rhy_n;
             }
+            if constexpr (DIAG) {   // Bx^2 = (dyA / ℑy h)^2 at cfc (li, ln): the next row's sqx_s
+                const double bxf = ((cA[0] - cA[-W]) * p.rdy) * rhy_n;
+                sqx_n = bxf * bxf;
+                if (it < 0) {       // By^2 at fcc (li, lj0-1) seeds the bracket of the first row
+                    const double byf = ((cA[-W] - RAW(s_A, li - 1, lj)) * p.rdx) * frcp(0.5 * (RAW(s_h, li - 1, lj) + RAW(s_h, li, lj)));
+                    sqy_s = byf * byf;
+                }
+            }
         }
         if (it >= 0) {
             // ---- x side: F_uu - Lxx at ccc li-1, F_uv - Lxy at ffc li, tracer flux at fcc li ---------------------
             const double uc = RAW(s_u, li, lj), ue = RAW(s_u, li + 1, lj), us = RAW(s_u, li, lj - 1);
-            double Fuu_w, Fuv_w, Tx_w, uq_w;
+            double Fuu_w, Fuv_w, Tx_w, uq_w, rhx_d;
             {
                 double vel[3];
                 vel[0] = sym4(RAW(s_u, li - 2, lj), RAW(s_u, li - 1, lj), uc, ue);
@@ -680,10 +691,29 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                     const double rhx = rc[3];
                     Tx_w = (p.dy * fl[2]) * rhx;
                     uq_w = uc * rhx;
+                    rhx_d = rhx;
                 }
             }
             const double Fuu_e = __shfl_down_sync(0xffffffffu, Fuu_w, 1), Fuv_e = __shfl_down_sync(0xffffffffu, Fuv_w, 1);
             const double Tx_e = __shfl_down_sync(0xffffffffu, Tx_w, 1), uq_e = __shfl_down_sync(0xffffffffu, uq_w, 1);
+            if constexpr (DIAG) {
+                // ---- energy sums and max |uh / ℑx h| (divergence_sw_mhd.jl:47,53,63-75), row lj ----------
+                // KE bracket uh^2 + ℑxyᶠᶜᵃ(vh^2) at fcc (li, lj), ME bracket Bx^2 + ℑxyᶜᶠᵃ(By^2) at cfc (li, lj); uq_w / uc is
+                // 1/ℑx h at fcc (li, lj); lane 31 is the column beyond the tile and supplies the east neighbours
+                const double Ac_ = RAW(s_A, li, lj), hs_ = RAW(s_h, li, lj - 1);
+                const double byf = ((Ac_ - RAW(s_A, li - 1, lj)) * p.rdx) * rhx_d;
+                const double sqy = byf * byf, csum = sqy_s + sqy;
+                const double v00 = RAW(s_v, li - 1, lj), v10 = RAW(s_v, li, lj), v01 = RAW(s_v, li - 1, ln), v11 = RAW(s_v, li, ln);
+                const double keb = fma(uc, uc, avg4(v00 * v00, v10 * v10, v01 * v01, v11 * v11));
+                const double csum_e = __shfl_down_sync(0xffffffffu, csum, 1), keb_e = __shfl_down_sync(0xffffffffu, keb, 1);
+                const double meb = fma(0.25, csum + csum_e, sqx_s);
+                if (it >= 1 && own && (j - 1 <= p.row_end)) me_acc = fma(0.25 * hs_, meb_s + meb, me_acc);   // cell (li, lj-1)
+                if (active) {
+                    ke_acc = fma(0.25 * RH(li, lj), keb + keb_e, ke_acc);                                     // (1/h)/2 (keb + keb_e)/2
+                    mu_acc = fmax(mu_acc, fabs(uq_w));
+                }
+                meb_s = meb; sqy_s = sqy;
+            }
 
             // ---- tendencies ----------------------------------------------------------------------
             // d(g h^2 / 2): h = 1 + O(1e-9) makes this a cancellation; keep the products un-contracted
@@ -734,77 +764,55 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
             }
         }
         Fvu_s = Fvu_n; Fvv_s = Fvv_c; Ty_s = Ty_n; vq_s = vq_n; rhff_s = rhff_n;
+        if constexpr (DIAG) sqx_s = sqx_n;
         gcell += (size_t)P;
     }
 
     // ---- fused diagnostics of the state at the start of the step ------------------------------
+    // KE, ME and max |uh / ℑx h| were accumulated in the row walk.  Left: the magnetic-energy bracket north of the warp's
+    // last row (one more reciprocal depth) and the quantities that need no reciprocal.
     if constexpr (DIAG) {
         double dg[NDIAG];
 #pragma unroll
         for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
         dg[6] = -INFINITY;
-        double *const s_red = smem + DERIVED_D + 2;
-        constexpr int NR = R + 2;                            // rows b = lj0-1 .. lj0+R, index k = b - (lj0-1)
-        auto sq = [](double x) { return x * x; };
-        double Ac[NR], Aw[NR], Ae[NR], sqy[NR], sqx[NR], rhx[NR];
-        {
-            double den[2 * NR - 1], rc[2 * NR - 1], hcol[NR];
-#pragma unroll
-            for (int k = 0; k < NR; k++) {
-                const int b = lj0 - 1 + k;
-                Ac[k] = RAW(s_A, li, b); Aw[k] = RAW(s_A, li - 1, b); Ae[k] = RAW(s_A, li + 1, b);
-                hcol[k] = RAW(s_h, li, b);
-                den[k] = 0.5 * (RAW(s_h, li - 1, b) + hcol[k]);                              // ℑx h at fcc(li, b)
+        if (warp_has_rows) {
+            {   // ME of the cell (li, lj0+R-1): bracket at cfc (li, lj0+R); its Bx^2 is sqx_s
+                const int lt = lj0 + R;
+                const double byf = ((RAW(s_A, li, lt) - RAW(s_A, li - 1, lt)) * p.rdx) * frcp(0.5 * (RAW(s_h, li - 1, lt) + RAW(s_h, li, lt)));
+                const double csum = fma(byf, byf, sqy_s);
+                const double csum_e = __shfl_down_sync(0xffffffffu, csum, 1);
+                const double meb = fma(0.25, csum + csum_e, sqx_s);
+                if (own && (jc0 + R - 1 <= p.row_end)) me_acc = fma(0.25 * RAW(s_h, li, lt - 1), meb_s + meb, me_acc);
             }
+            dg[0] = ke_acc; dg[1] = me_acc; dg[4] = mu_acc;
+            double Am[3], A0[3], Ap[3];                      // A at columns li-1, li, li+1 of rows lj-1, lj, lj+1 (sliding)
 #pragma unroll
-            for (int k = 1; k < NR; k++) den[NR + k - 1] = 0.5 * (hcol[k - 1] + hcol[k]);     // ℑy h at cfc(li, b)
-            rcp_n<2 * NR - 1>(den, rc);
+            for (int c = 0; c < 3; c++) { Am[c] = RAW(s_A, li - 1 + c, lj0 - 1); A0[c] = RAW(s_A, li - 1 + c, lj0); }
 #pragma unroll
-            for (int k = 0; k < NR; k++) { rhx[k] = rc[k]; sqy[k] = sq(((Ac[k] - Aw[k]) * p.rdx) * rc[k]); }   // (dxA / ℑx h)^2 at fcc
-            sqx[0] = 0.0;
+            for (int r = 0; r < R; r++) {
+                const int lj = lj0 + r;
 #pragma unroll
-            for (int k = 1; k < NR; k++) sqx[k] = sq(-((Ac[k] - Ac[k - 1]) * p.rdy) * rc[NR + k - 1]);          // (dyA / ℑy h)^2 at cfc
-        }
-        double uu[R], vc[R + 1], kb[R];
-        {
-            double vw2[R + 1], vc2[R + 1];
-#pragma unroll
-            for (int k = 0; k <= R; k++) { vc[k] = RAW(s_v, li, lj0 + k); vc2[k] = sq(vc[k]); vw2[k] = sq(RAW(s_v, li - 1, lj0 + k)); }
-#pragma unroll
-            for (int r = 0; r < R; r++) {                    // KE bracket uh^2 + ℑxyᶠᶜᵃ(vh^2) at fcc(li)
-                uu[r] = RAW(s_u, li, lj0 + r);
-                kb[r] = sq(uu[r]) + avg4(vw2[r], vc2[r], vw2[r + 1], vc2[r + 1]);
-            }
-        }
-        double sqye[NR], kbe[R];                             // east neighbours (lane 31 holds the column beyond the tile)
-#pragma unroll
-        for (int k = 0; k < NR; k++) sqye[k] = __shfl_down_sync(0xffffffffu, sqy[k], 1);
-#pragma unroll
-        for (int r = 0; r < R; r++) kbe[r] = __shfl_down_sync(0xffffffffu, kb[r], 1);
-        double mb[R + 1];
-#pragma unroll
-        for (int k = 1; k < NR; k++) mb[k - 1] = sqx[k] + avg4(sqy[k - 1], sqye[k - 1], sqy[k], sqye[k]);
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int j = jc0 + r, k = r + 1, lj = lj0 + r;
-            if (own && (j <= p.row_end)) {
-                const double hh = RAW(s_h, li, lj), aa = Ac[k], rh = RH(li, lj);
-                dg[0] += (0.5 * rh) * (0.5 * (kb[r] + kbe[r]));
-                dg[1] += (0.5 * hh) * (0.5 * (mb[r] + mb[r + 1]));
-                const double dh = hh - p.h_ref;
-                dg[2] += (0.5 * p.g) * (dh * dh);
-                dg[3] += hh;
-                dg[4] = fmax(dg[4], fabs(uu[r] * rhx[k]));
-                dg[5] = fmax(dg[5], fabs(aa));
-                dg[6] = fmax(dg[6], -hh);
-                {
-                    const double hbx0 = (Aw[k - 1] + Ac[k - 1]) - (Aw[k + 1] + Ac[k + 1]), hbx1 = (Ac[k - 1] + Ae[k - 1]) - (Ac[k + 1] + Ae[k + 1]);
-                    const double hby0 = (Ae[k - 1] + Ae[k]) - (Aw[k - 1] + Aw[k]), hby1 = (Ae[k] + Ae[k + 1]) - (Aw[k] + Aw[k + 1]);
-                    dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
+                for (int c = 0; c < 3; c++) Ap[c] = RAW(s_A, li - 1 + c, lj + 1);
+                if (own && (jc0 + r <= p.row_end)) {
+                    const double hh = RAW(s_h, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj), aa = A0[1];
+                    const double dh = hh - p.h_ref;
+                    dg[2] = fma(0.5 * p.g, dh * dh, dg[2]);
+                    dg[3] += hh;
+                    dg[5] = fmax(dg[5], fabs(aa));
+                    dg[6] = fmax(dg[6], -hh);
+                    {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
+                        const double hbx0 = (Am[0] + Am[1]) - (Ap[0] + Ap[1]), hbx1 = (Am[1] + Am[2]) - (Ap[1] + Ap[2]);
+                        const double hby0 = (Am[2] + A0[2]) - (Am[0] + A0[0]), hby1 = (A0[2] + Ap[2]) - (A0[0] + Ap[0]);
+                        dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
+                    }
+                    if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) dg[8] += 1.0;
                 }
-                if (!(isfinite(hh) && isfinite(aa) && isfinite(uu[r]) && isfinite(vc[r]))) dg[8] += 1.0;
+#pragma unroll
+                for (int c = 0; c < 3; c++) { Am[c] = A0[c]; A0[c] = Ap[c]; }
             }
         }
+        double *const s_red = smem + DERIVED_D + 2;
 #pragma unroll
         for (int q = 0; q < NDIAG; q++) {
             const bool is_max = (q >= 4 && q <= 7);

@@ -29,10 +29,7 @@ def test_row_blocked_kernels_fit_four_ctas_per_sm():
     assert set(ks) == {(f, s, 0) for f in ("rb", "rbd") for s in (1, 2, 3)} | {("rb", 1, 1), ("rbd", 1, 1)}
     for key, k in ks.items():
         assert k["regs"] <= 128, (key, k)           # 65536 registers / (4 CTAs x 128 threads)
-        # the plain kernels (3 of 3 launches per step without diagnostics, 2 of 3 with) may not spill at all; the
-        # DIAG variants may park a few words in their once-per-warp diagnostic tail, never in the row loop
-        limit = 64 if key[2] == 1 else 0
-        assert k["spill"] <= limit and k["stack"] <= limit, (key, k)
+        assert k["spill"] == 0 and k["stack"] == 0, (key, k)
 
 
 def test_shared_memory_layout_fits_four_ctas_per_sm():
@@ -41,7 +38,7 @@ def test_shared_memory_layout_fits_four_ctas_per_sm():
     TX, TYB, R = 32, macro("RB_TY"), macro("RB_R")
     NW, NDIAG = TYB // R, 9
     SZP = ((TX + 6) * (TYB + 6) * 8 + 127) // 128 * 16
-    jac = 4 * SZP + 3 * (TX + 5) * (TYB + 5) + 2 * (TX + 2) * (TYB + 2) + 2 + NW * NDIAG
+    jac = 4 * SZP + 3 * (TX + 5) * (TYB + 5) + 2 * (TX + 2) * (TYB + 2) + 2 + NW * (4 * R + 2)    # per-warp east-column scratch
     div = 4 * SZP + 4 * (TX + 4) * (TYB + 4) + (TX + 2) * (TYB + 2) + 2 + NW * NDIAG
     assert "constexpr int DERIVED = o_By + NC;" in SRC and "constexpr int DERIVED_D = 4 * NB + NRH;" in SRC
     budget = (228 * 1024 - 4 * 1024) // 4           # 228 KB per SM, 1 KB reserved per resident CTA

@@ -2,6 +2,7 @@
 Bounded-y figures (energy_plots/*/{64x64,128x128}_low_B_low_U.png, digitised in tests/golden/published_traces.json;
 IC: divergence_sw_mhd.jl:17,34-37).  Oracle switches (include/swmhd.h, oracle only):
 
+    (plus, outside C10: JS weights, centred tracer advection, WENO eps = 3e-4)
     D1  SWMHD_FLAG_BC_DEPTH1   no-flux / gradient BCs fill only the first halo row (deeper rows untouched)
     W3  SWMHD_FLAG_WALL_WENO3  WENO3 one cell further from the wall than the centred-2nd-order fallback needs
     VM  SWMHD_FLAG_V_MIRROR    v|vh beyond the wall: odd mirror instead of untouched cells
@@ -28,10 +29,10 @@ FIGS = [(J, 64, None), (D, 64, GRAD), (J, 128, GRAD), (D, 128, GRAD)]      # BC 
 FLAGS = [("D1", abi.FLAG_BC_DEPTH1), ("W3", abi.FLAG_WALL_WENO3), ("VM", abi.FLAG_V_MIRROR)]
 
 
-def run(form, N, grad, flags, T=14.5, dt=0.01):
+def run(form, N, grad, flags, T=14.5, dt=0.01, eps=1e-6):
     g, _, U = make_case("BJ" if form == J else "BD", N)
     cfg = abi.make_config(g.Nx, g.Ny, formulation=abi.JACOBIAN if form == J else abi.DIVERGENCE, flags=flags,
-                          topo_y=abi.BOUNDED, A_gradient=grad)
+                          topo_y=abi.BOUNDED, A_gradient=grad, weno_eps=eps)
     O.fill_halos(cfg, U)
     pub = TR[f"{form}/{N}x{N}_low_B_low_U"]
     worst = {k: 0.0 for k in ("ke", "me", "pe")}
@@ -61,6 +62,12 @@ def main():
                 cells.append(None); continue
             w = run(form, N, grad, flags)
             cells.append(w)
+        rows.append((label, cells))
+        print(label, ["-" if c is None else "KE %.1e ME %.1e PE %.1e" % (c["ke"], c["me"], c["pe"]) for c in cells], flush=True)
+    # not wall semantics: what else could keep more magnetic energy at 64^2?
+    for label, flags, eps in [("JS weights (C1)", abi.FLAG_WENO_JS, 1e-6), ("A: centred 2nd order", abi.FLAG_TRACER_CEN2, 1e-6),
+                              ("A: centred 4th order", abi.FLAG_TRACER_CEN4, 1e-6), ("WENO eps = 3e-4 (C2)", 0, 3e-4)]:
+        cells = [None if ("--quick" in sys.argv and N == 128) else run(form, N, grad, flags, eps=eps) for form, N, grad in FIGS]
         rows.append((label, cells))
         print(label, ["-" if c is None else "KE %.1e ME %.1e PE %.1e" % (c["ke"], c["me"], c["pe"]) for c in cells], flush=True)
     print("\n| switches | " + " | ".join(f"{'Jac' if f == J else 'Div'} {N}² (KE / ME / PE)" for f, N, _ in FIGS) + " |")
