@@ -214,4 +214,37 @@ __device__ __forceinline__ void rcp_mix_n(const double (&x)[N], double (&r)[N]) 
 // every normal x (positive denormals below 2^-1042 count as zero; they select the other upwind side of a
 // flux that is then multiplied by that denormal).
 __device__ __forceinline__ bool gt0(double x) { return __double2hiint(x) > 0; }
+
+// ---- warp reduction of the fused diagnostics -------------------------------------------------------------
+// Extrema travel as order-preserving 64-bit keys (key(x) < key(y) <=> x < y for all non-NaN doubles; NaN sorts
+// above +inf), so that the warp maximum is two REDUX instructions (high word, then the low words of the lanes that
+// hold the maximal high word) instead of a five-step shuffle tree of emulated FP64 maxima.
+__device__ __forceinline__ unsigned long long ord_key(double x) {
+    const long long b = __double_as_longlong(x);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double ord_val(unsigned long long k) {
+    return __longlong_as_double((long long)((k >> 63) ? (k ^ 0x8000000000000000ull) : ~k));
+}
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long k) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return ((unsigned long long)mh << 32) | ml;
+}
+// Four sums at once: a reduce-scatter over the lanes (each step halves the quantities a lane carries), 6 shuffles
+// instead of 20.  The totals of q[0..3] end up in lanes 0, 8, 16, 24 (returned in every lane of those groups' leaders);
+// the summation order is fixed by the lane numbers: bit-reproducible.
+__device__ __forceinline__ double warp_sum4(const double (&q)[4], int lane) {
+    const bool up16 = lane & 16, up8 = lane & 8;
+    const double k0 = up16 ? q[2] : q[0], k1 = up16 ? q[3] : q[1];
+    const double s0 = up16 ? q[0] : q[2], s1 = up16 ? q[1] : q[3];
+    const double r0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 16);
+    const double r1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 16);
+    double r = (up8 ? r1 : r0) + __shfl_xor_sync(0xffffffffu, up8 ? r0 : r1, 8);
+    r += __shfl_xor_sync(0xffffffffu, r, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    return r;           // lanes 0..7: q[0], 8..15: q[1], 16..23: q[2], 24..31: q[3]
+}
 } // namespace swmhd

@@ -386,10 +386,10 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     // (two more reciprocal depths), and the quantities that need no reciprocal (PE, mass, extrema, div(hB), finite
     // flag), evaluated per thread for its R cells from the raw tile.
     if constexpr (DIAG) {
-        double dg[NDIAG];
-#pragma unroll
-        for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
-        dg[6] = -INFINITY;
+        double sums[4] = {0.0, 0.0, 0.0, 0.0};                // ke, me, pe, sum h
+        const unsigned long long kneut = ord_key(-INFINITY);
+        unsigned long long kmax[4] = {ord_key(0.0), ord_key(0.0), kneut, ord_key(0.0)};   // |u|, |A|, -h, |div hB| as ordered keys
+        bool bad = false;
         if (warp_has_rows) {
             {   // ME of the cell (li, lj0+R-1): bracket at cfc (li, lj0+R)
                 const int lt = lj0 + R;
@@ -403,42 +403,53 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
                 const double meb = fma(0.25, csum + csum_e, bxf * bxf);
                 if (col_ok && (jc0 + R - 1 <= p.row_end)) me_acc = fma(0.25 * hC, meb_s + meb, me_acc);
             }
-            dg[0] = ke_acc; dg[1] = me_acc;
+            sums[0] = ke_acc; sums[1] = me_acc;
             double Am[3], A0[3], Ap[3];                      // A at columns li-1, li, li+1 of rows lj-1, lj, lj+1 (sliding)
 #pragma unroll
             for (int c = 0; c < 3; c++) { Am[c] = RAW(s_A, li - 1 + c, lj0 - 1); A0[c] = RAW(s_A, li - 1 + c, lj0); }
 #pragma unroll
-            for (int r = 0; r < R; r++) {
+            for (int r = 0; r < R; r++) {            // branch-free: cells beyond the launch contribute neutral elements
                 const int lj = lj0 + r;
 #pragma unroll
                 for (int c = 0; c < 3; c++) Ap[c] = RAW(s_A, li - 1 + c, lj + 1);
-                if (col_ok && (jc0 + r <= p.row_end)) {
-                    const double hh = RAW(s_h, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj), aa = A0[1];
-                    const double dh = hh - p.h_ref;
-                    dg[2] = fma(0.5 * p.g, dh * dh, dg[2]);
-                    dg[3] += hh;
-                    dg[4] = fmax(dg[4], fabs(uu));
-                    dg[5] = fmax(dg[5], fabs(aa));
-                    dg[6] = fmax(dg[6], -hh);
-                    {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
-                        const double hbx0 = (Am[0] + Am[1]) - (Ap[0] + Ap[1]), hbx1 = (Am[1] + Am[2]) - (Ap[1] + Ap[2]);
-                        const double hby0 = (Am[2] + A0[2]) - (Am[0] + A0[0]), hby1 = (A0[2] + Ap[2]) - (A0[0] + Ap[0]);
-                        dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
-                    }
-                    if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) dg[8] += 1.0;
+                const bool ok = col_ok && (jc0 + r <= p.row_end);
+                const double hh = RAW(s_h, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj), aa = A0[1];
+                const double dh = hh - p.h_ref;
+                sums[2] = fma(ok ? (0.5 * p.g) * dh : 0.0, dh, sums[2]);
+                sums[3] += ok ? hh : 0.0;
+                kmax[0] = max(kmax[0], ok ? ord_key(fabs(uu)) : kneut);
+                kmax[1] = max(kmax[1], ok ? ord_key(fabs(aa)) : kneut);
+                kmax[2] = max(kmax[2], ok ? ord_key(-hh) : kneut);
+                {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
+                    const double hbx0 = (Am[0] + Am[1]) - (Ap[0] + Ap[1]), hbx1 = (Am[1] + Am[2]) - (Ap[1] + Ap[2]);
+                    const double hby0 = (Am[2] + A0[2]) - (Am[0] + A0[0]), hby1 = (A0[2] + Ap[2]) - (A0[0] + Ap[0]);
+                    const double dv = fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy);
+                    kmax[3] = max(kmax[3], ok ? ord_key(dv) : kneut);
                 }
+                // finite <=> exponent field below 0x7ff: one integer test on the OR of the four high words' exponent overflow
+                const unsigned eh = (unsigned)__double2hiint(hh) & 0x7ff00000u, ea = (unsigned)__double2hiint(aa) & 0x7ff00000u;
+                const unsigned eu = (unsigned)__double2hiint(uu) & 0x7ff00000u, ev = (unsigned)__double2hiint(vv) & 0x7ff00000u;
+                bad = bad || (ok && (eh == 0x7ff00000u || ea == 0x7ff00000u || eu == 0x7ff00000u || ev == 0x7ff00000u));
 #pragma unroll
                 for (int c = 0; c < 3; c++) { Am[c] = A0[c]; A0[c] = Ap[c]; }
             }
         }
-        // fixed-order reduction: R cells per thread (above), warp tree, then the warps in order
+        // fixed-order reduction: R cells per thread (above), the warp (four sums by reduce-scatter, four extrema by REDUX
+        // on ordered keys, the finite flag by vote), then the warps in order
         double *const s_red = smem + DERIVED + 2;            // warp w's partials at the start of its scratch slice
-        __syncwarp();                                        // lane 31 has read the last east-column values
+        __syncwarp();
+        {
+            const double tot = warp_sum4(sums, lane);
+            unsigned long long km[4];
 #pragma unroll
-        for (int q = 0; q < NDIAG; q++) {
-            const bool is_max = (q >= 4 && q <= 7);
-            const double x = is_max ? warp_max(dg[q]) : warp_sum(dg[q]);
-            if (lane == 0) s_red[wp * NE + q] = x;
+            for (int q = 0; q < 4; q++) km[q] = warp_max_key(kmax[q]);
+            const bool anybad = __any_sync(0xffffffffu, bad);
+            if ((lane & 7) == 0) s_red[wp * NE + (lane >> 3)] = tot;
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) s_red[wp * NE + 4 + q] = ord_val(km[q]);
+                s_red[wp * NE + 8] = anybad ? 1.0 : 0.0;
+            }
         }
         __syncthreads();
         if (tid < NDIAG) {
@@ -772,10 +783,10 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
     // KE, ME and max |uh / ℑx h| were accumulated in the row walk.  Left: the magnetic-energy bracket north of the warp's
     // last row (one more reciprocal depth) and the quantities that need no reciprocal.
     if constexpr (DIAG) {
-        double dg[NDIAG];
-#pragma unroll
-        for (int q = 0; q < NDIAG; q++) dg[q] = 0.0;
-        dg[6] = -INFINITY;
+        double sums[4] = {0.0, 0.0, 0.0, 0.0};                // ke, me, pe, sum h
+        const unsigned long long kneut = ord_key(-INFINITY);
+        unsigned long long kmax[4] = {ord_key(0.0), ord_key(0.0), kneut, ord_key(0.0)};   // |u|, |A|, -h, |div hB| as ordered keys
+        bool bad = false;
         if (warp_has_rows) {
             {   // ME of the cell (li, lj0+R-1): bracket at cfc (li, lj0+R); its Bx^2 is sqx_s
                 const int lt = lj0 + R;
@@ -785,45 +796,61 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
                 const double meb = fma(0.25, csum + csum_e, sqx_s);
                 if (own && (jc0 + R - 1 <= p.row_end)) me_acc = fma(0.25 * RAW(s_h, li, lt - 1), meb_s + meb, me_acc);
             }
-            dg[0] = ke_acc; dg[1] = me_acc; dg[4] = mu_acc;
+            sums[0] = ke_acc; sums[1] = me_acc;
+            kmax[0] = ord_key(mu_acc);
             double Am[3], A0[3], Ap[3];                      // A at columns li-1, li, li+1 of rows lj-1, lj, lj+1 (sliding)
 #pragma unroll
             for (int c = 0; c < 3; c++) { Am[c] = RAW(s_A, li - 1 + c, lj0 - 1); A0[c] = RAW(s_A, li - 1 + c, lj0); }
 #pragma unroll
-            for (int r = 0; r < R; r++) {
+            for (int r = 0; r < R; r++) {            // branch-free: cells beyond the launch contribute neutral elements
                 const int lj = lj0 + r;
 #pragma unroll
                 for (int c = 0; c < 3; c++) Ap[c] = RAW(s_A, li - 1 + c, lj + 1);
-                if (own && (jc0 + r <= p.row_end)) {
-                    const double hh = RAW(s_h, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj), aa = A0[1];
-                    const double dh = hh - p.h_ref;
-                    dg[2] = fma(0.5 * p.g, dh * dh, dg[2]);
-                    dg[3] += hh;
-                    dg[5] = fmax(dg[5], fabs(aa));
-                    dg[6] = fmax(dg[6], -hh);
-                    {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
-                        const double hbx0 = (Am[0] + Am[1]) - (Ap[0] + Ap[1]), hbx1 = (Am[1] + Am[2]) - (Ap[1] + Ap[2]);
-                        const double hby0 = (Am[2] + A0[2]) - (Am[0] + A0[0]), hby1 = (A0[2] + Ap[2]) - (A0[0] + Ap[0]);
-                        dg[7] = fmax(dg[7], fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy));
-                    }
-                    if (!(isfinite(hh) && isfinite(aa) && isfinite(uu) && isfinite(vv))) dg[8] += 1.0;
+                const bool ok = own && (jc0 + r <= p.row_end);
+                const double hh = RAW(s_h, li, lj), uu = RAW(s_u, li, lj), vv = RAW(s_v, li, lj), aa = A0[1];
+                const double dh = hh - p.h_ref;
+                sums[2] = fma(ok ? (0.5 * p.g) * dh : 0.0, dh, sums[2]);
+                sums[3] += ok ? hh : 0.0;
+                kmax[1] = max(kmax[1], ok ? ord_key(fabs(aa)) : kneut);
+                kmax[2] = max(kmax[2], ok ? ord_key(-hh) : kneut);
+                {   // div(hB) at ccc, telescoped ℑxy∂ (pure round-off)
+                    const double hbx0 = (Am[0] + Am[1]) - (Ap[0] + Ap[1]), hbx1 = (Am[1] + Am[2]) - (Ap[1] + Ap[2]);
+                    const double hby0 = (Am[2] + A0[2]) - (Am[0] + A0[0]), hby1 = (A0[2] + Ap[2]) - (A0[0] + Ap[0]);
+                    const double dv = fabs((hbx1 - hbx0) * (0.25 * p.rdy) * p.rdx + (hby1 - hby0) * (0.25 * p.rdx) * p.rdy);
+                    kmax[3] = max(kmax[3], ok ? ord_key(dv) : kneut);
                 }
+                // finite <=> exponent field below 0x7ff: one integer test on the OR of the four high words' exponent overflow
+                const unsigned eh = (unsigned)__double2hiint(hh) & 0x7ff00000u, ea = (unsigned)__double2hiint(aa) & 0x7ff00000u;
+                const unsigned eu = (unsigned)__double2hiint(uu) & 0x7ff00000u, ev = (unsigned)__double2hiint(vv) & 0x7ff00000u;
+                bad = bad || (ok && (eh == 0x7ff00000u || ea == 0x7ff00000u || eu == 0x7ff00000u || ev == 0x7ff00000u));
 #pragma unroll
                 for (int c = 0; c < 3; c++) { Am[c] = A0[c]; A0[c] = Ap[c]; }
             }
         }
-        double *const s_red = smem + DERIVED_D + 2;
+        // fixed-order reduction: R cells per thread (above), the warp (four sums by reduce-scatter, four extrema by REDUX
+        // on ordered keys, the finite flag by vote), then the warps in order
+        double *const s_red = smem + DERIVED_D + 2;            // warp w's partials at the start of its scratch slice
+        __syncwarp();
+        {
+            const double tot = warp_sum4(sums, lane);
+            unsigned long long km[4];
 #pragma unroll
-        for (int q = 0; q < NDIAG; q++) {
-            const bool is_max = (q >= 4 && q <= 7);
-            const double x = is_max ? warp_max(dg[q]) : warp_sum(dg[q]);
-            if (lane == 0) s_red[wp * NDIAG + q] = x;
+            for (int q = 0; q < 4; q++) km[q] = warp_max_key(kmax[q]);
+            const bool anybad = __any_sync(0xffffffffu, bad);
+            if ((lane & 7) == 0) s_red[wp * NDIAG + (lane >> 3)] = tot;
+            if (lane == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; q++) s_red[wp * NDIAG + 4 + q] = ord_val(km[q]);
+                s_red[wp * NDIAG + 8] = anybad ? 1.0 : 0.0;
+            }
         }
         __syncthreads();
         if (tid < NDIAG) {
             const bool is_max = (tid >= 4 && tid <= 7);
             double acc = s_red[tid];
             for (int w2 = 1; w2 < NW; w2++) { const double x = s_red[w2 * NDIAG + tid]; acc = is_max ? fmax(acc, x) : acc + x; }
+            // partial slots are indexed by 8-row tile rows (the launch granularity of the host side): this
+            // tile fills its first slot and neutral elements into the others it covers
             const int tr8 = row0 / 8;
             p.diag[((size_t)tr8 * tiles_x + tile_x) * NDIAG + tid] = acc;
             for (int s2 = 1; s2 < TYB / 8; s2++)

@@ -213,3 +213,39 @@ def test_bounded_walls_keep_v_zero_and_halos_mirror():
 
 
 # B.3 (published energy traces): tests/test_published_traces.py, all twelve figures, machine-digitised.
+
+
+def test_c10_probe_switches_act_on_the_wall_rows_only():
+    """The C10 probe switches (tools/probe_c10.py, profiles/r02_c10_probe.md) change what they say they change:
+    D1 leaves the 2nd and 3rd halo rows of centre fields untouched, VM mirrors v oddly beyond the wall, W3 changes
+    tendencies only in the rows whose WENO5 footprint crosses a wall — and none of them touches a periodic grid."""
+    from cases import make_case
+    g, cfg, U = make_case("BJ", 40, Ny=24, perturb=3)
+    base = [u.copy() for u in U]
+    O.fill_halos(cfg, base)
+    G0 = O.tendencies(cfg, base)
+    for flag in (abi.FLAG_BC_DEPTH1, abi.FLAG_WALL_WENO3, abi.FLAG_V_MIRROR):
+        c = abi.Config.from_buffer_copy(cfg)
+        c.flags = flag
+        V = [u.copy() for u in U]
+        O.fill_halos(c, V)
+        if flag == abi.FLAG_BC_DEPTH1:
+            assert np.array_equal(V[abi.A][2], base[abi.A][2]) and np.all(V[abi.A][0:2, 3:-3] == 0.0)     # k = 1 filled, k = 2, 3 untouched
+        if flag == abi.FLAG_V_MIRROR:
+            assert np.array_equal(V[abi.V][2, 3:-3], -base[abi.V][4, 3:-3]) and np.any(V[abi.V][2] != 0.0)
+        if flag == abi.FLAG_WALL_WENO3:
+            G = O.tendencies(c, base)
+            rows = np.unique(np.nonzero(G[abi.H][3:-3, 3:-3] != G0[abi.H][3:-3, 3:-3])[0])
+            assert len(rows) and set(rows) <= {1, 2, g.Ny - 3, g.Ny - 2}, rows      # faces 3 and Ny-1: cells 2, 3 and Ny-2, Ny-1 (0-based 1, 2, Ny-3, Ny-2)
+    gp, cfgp, Up = make_case("J", 40, Ny=24, perturb=3)
+    ref = [u.copy() for u in Up]
+    O.fill_halos(cfgp, ref)
+    for flag in (abi.FLAG_BC_DEPTH1, abi.FLAG_WALL_WENO3, abi.FLAG_V_MIRROR):
+        c = abi.Config.from_buffer_copy(cfgp)
+        c.flags = flag
+        V = [u.copy() for u in Up]
+        O.fill_halos(c, V)
+        O.step(c, V, 0.004, 1)
+        W = [u.copy() for u in ref]
+        O.step(cfgp, W, 0.004, 1)
+        assert all(np.array_equal(a, b) for a, b in zip(V, W))
