@@ -213,6 +213,17 @@ class Env:
             raise SystemExit("bench.py needs a CUDA device: the SWMHD hot path has no CPU fallback")
         torch.cuda.set_device(self.local)
         self.dev = f"cuda:{self.local}"
+        self.numa = None
+        if self.world > 1:
+            # N ranks push their slabs through the host at once in the e2e leg: keep this rank (and the pinned pages it
+            # first-touches) on the CPUs / NUMA node next to its GPU.  Not at N = 1: the CPU baseline wants every core.
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.local))
+                self.numa = f"cpu affinity of GPU {self.local}: {len(os.sched_getaffinity(0))} cpus"
+            except Exception as ex:
+                self.numa = f"unset ({type(ex).__name__})"
         self.dist = None
         if self.world > 1:
             import torch.distributed as dist
@@ -405,8 +416,8 @@ def e2e_slabs(env, leg, K):
     return {"value": leg.Nx * leg.NyG * ke / el, "unit": UNIT, "h2d_bytes_per_step": h2d * env.world, "d2h_bytes_per_step": 9 * 8 * env.world,
             "ms_per_step": el / ke * 1e3, "steps": ke,
             "what": "per rank: slab upload from pinned host memory (4 haloed fields) + NCCL halo exchange + one RK3 step + ring-reduced diagnostics to host, per step",
-            "bound": "host side: every rank pushes its slab through the host's PCIe root complexes / memory controllers at once "
-                     "(pinned buffers are not NUMA-placed per rank)"}
+            "bound": "host side: every rank pushes its slab through the host's PCIe root complexes / memory controllers at once",
+            "numa": env.numa}
 
 
 def slab_parity(env):

@@ -4,10 +4,10 @@
 N=${1:-2}; K=${2:-20}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 300 python -m pytest tests/test_gpu_round2.py -m gpu -q -k "n_gpus or second_device" 2>&1 | tail -8 | tee gpurun_out/pytest_multi_n$N.log
+timeout 150 python -m pytest tests/test_gpu_round2.py -m gpu -q -k "n_gpus or second_device" 2>&1 | tail -8 | tee gpurun_out/pytest_multi_n$N.log
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531"
-timeout 300 $TR tools/gpu_multi_test.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -12 | tee gpurun_out/multi_test_n$N.log
-timeout 420 $TR bench.py --gpus $N --steps $K --warmup 5 2> gpurun_out/bench_n$N.err > gpurun_out/bench_n$N.json; echo "bench rc=$?"
+timeout 150 $TR tools/gpu_multi_test.py 2>&1 | grep -v "^W\|^\*\*\*" | tail -12 | tee gpurun_out/multi_test_n$N.log
+timeout 330 $TR bench.py --gpus $N --steps $K --warmup 5 2> gpurun_out/bench_n$N.err > gpurun_out/bench_n$N.json; echo "bench rc=$?"
 tail -5 gpurun_out/bench_n$N.err
 python - <<PY
 import json
