@@ -157,6 +157,18 @@ int  swmhd_step(swmhd_ctx *ctx, double dt, int nsteps);
    the stage-1 kernel at no extra HBM traffic and written to diags[0..nsteps) */
 int  swmhd_step_diag(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags);
 
+/* set!(model, u, v, h, A) + time_step!(model, dt) (+ the diagnostics of the uploaded state when diag != NULL) in one call:
+   the upload of the four parent arrays (page-locked for real overlap: swmhd_pin_host) is pipelined with stage 1 by row
+   bands, so that only the first and last band of stage 1 run after the last byte has crossed the PCIe link.
+   host[k] holds n_each >= swmhd_field_len(ctx, k) doubles; halos of the host arrays need not be filled.  Single slab. */
+int  swmhd_upload_step(swmhd_ctx *ctx, const double *const host[4], size_t n_each, double dt, swmhd_diag *diag);
+
+/* A batch of steps with a per-step dt: run!(simulation) clips dt to the next TimeInterval(0.1) output and to stop_time
+   (upstream aligned_time_step; SWMHD_example.jl:42,81-84,97), so the step sizes between two output times are
+   dt, dt, ..., remainder.  The host plans the sequence (the clock ticks (8/15, 2/15, 1/3) dt per stage, replayable in
+   floating point) and the device runs it without returning in between.  diags may be NULL; else diags[0..nsteps). */
+int  swmhd_step_seq(swmhd_ctx *ctx, const double *dts, int nsteps, swmhd_diag *diags);
+
 /* one RK3 substage (stage = 1,2,3), including the halo fill that follows it */
 int  swmhd_substage(swmhd_ctx *ctx, double dt, int stage);
 /* calculate_tendencies!(model): G^n of the current state into four host parent arrays, each of

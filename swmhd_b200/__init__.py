@@ -10,7 +10,7 @@ from .models import (  # noqa: F401
     ShallowWaterModel, VectorInvariantFormulation, ConservativeFormulation, WENO5, VelocityStencil,
     VorticityStencil, FPlane, Forcing, FieldBoundaryConditions, GradientBoundaryCondition,
     lorentz_force_func_x, lorentz_force_func_y, div_lorentz_x, div_lorentz_y,
-    set_b, time_step_b, time_step_diag_b, run_b, Simulation, Callback, IterationInterval, TimeInterval, MemoryOutputWriter,
+    set_b, time_step_b, time_step_diag_b, set_and_step_diag_b, run_b, Simulation, Callback, IterationInterval, TimeInterval, MemoryOutputWriter,
 )
 
 __version__ = "0.1.0"

@@ -99,6 +99,8 @@ SYMBOLS = [
     ("swmhd_fill_halos", C.c_int, [_ctx]),
     ("swmhd_step", C.c_int, [_ctx, C.c_double, C.c_int]),
     ("swmhd_step_diag", C.c_int, [_ctx, C.c_double, C.c_int, C.POINTER(Diag)]),
+    ("swmhd_upload_step", C.c_int, [_ctx, C.POINTER(_dp), C.c_size_t, C.c_double, C.POINTER(Diag)]),
+    ("swmhd_step_seq", C.c_int, [_ctx, C.POINTER(C.c_double), C.c_int, C.POINTER(Diag)]),
     ("swmhd_substage", C.c_int, [_ctx, C.c_double, C.c_int]),
     ("swmhd_tendencies", C.c_int, [_ctx, C.POINTER(_dp), C.c_size_t]),
     ("swmhd_diagnostics", C.c_int, [_ctx, C.POINTER(Diag)]),

@@ -88,6 +88,21 @@ class Context:
         self._ck(self.lib.swmhd_step_diag(self._h, float(dt), int(nsteps), arr))
         return [d.as_dict() for d in arr]
 
+    def upload_step(self, U, dt, diag=True):
+        """set_state(U) + one RK3 step (+ diagnostics of the uploaded state), the upload pipelined with stage 1."""
+        arr = (_dp * 4)(*[_ptr(u) for u in U])
+        d = abi.Diag() if diag else None
+        self._ck(self.lib.swmhd_upload_step(self._h, arr, max(u.size for u in U), float(dt), C.byref(d) if diag else None))
+        return d.as_dict() if diag else None
+
+    def step_seq(self, dts, diag=False):
+        """One call, len(dts) RK3 steps, step n with dts[n] (the aligned Δt sequence up to the next output time)."""
+        n = len(dts)
+        arr = (C.c_double * n)(*[float(x) for x in dts])
+        dg = (abi.Diag * n)() if diag else None
+        self._ck(self.lib.swmhd_step_seq(self._h, arr, n, dg))
+        return [d.as_dict() for d in dg] if diag else None
+
     def step_profile(self, dt, nsteps=1, diag=False):
         """Mean device time (ms) of the three fused substage kernels over nsteps steps
         (diag=True: with the diagnostics fused into stage 1, as step_diag runs them)."""

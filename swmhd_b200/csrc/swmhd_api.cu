@@ -716,7 +716,8 @@ extern "C" int swmhd_diagnostics(swmhd_ctx *ctx, swmhd_diag *out) {
 }
 
 // ---- stepping ---------------------------------------------------------------------------------------------
-static int step_impl(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags) {
+// nsteps RK3 steps; step n uses dts[n] when dts is given, else dt
+static int step_impl(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags, const double *dts = nullptr) {
     if (!ctx) return SWMHD_ERR_ARG;
     if (nsteps < 0) return fail(ctx, SWMHD_ERR_ARG, "nsteps < 0");
     if (ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "a host-driven substage is in flight");
@@ -731,7 +732,8 @@ static int step_impl(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags) {
         if (diags && chunk > ctx->diag_slots) chunk = ctx->diag_slots;
         for (int n = 0; n < chunk; n++) {
             // diagnostics of the state at the start of the step: fused into the stage-1 kernel
-            for (int st = 1; st <= 3; st++) { rc = substage_async(ctx, dt, st, nullptr, nullptr, diags ? n : -1); if (rc) return rc; }
+            const double dtn = dts ? dts[done + n] : dt;
+            for (int st = 1; st <= 3; st++) { rc = substage_async(ctx, dtn, st, nullptr, nullptr, diags ? n : -1); if (rc) return rc; }
         }
         if (diags) {
             rc = fetch_diag(ctx, 0, chunk, true, host);
@@ -755,9 +757,114 @@ static int step_impl(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags) {
 }
 
 extern "C" int swmhd_step(swmhd_ctx *ctx, double dt, int nsteps) { return step_impl(ctx, dt, nsteps, nullptr); }
+extern "C" int swmhd_step_seq(swmhd_ctx *ctx, const double *dts, int nsteps, swmhd_diag *diags) {
+    if (!ctx) return SWMHD_ERR_ARG;
+    if (!dts && nsteps > 0) return fail(ctx, SWMHD_ERR_ARG, "dts is null");
+    for (int n = 0; n < nsteps; n++)
+        if (!(dts[n] > 0.0) || !std::isfinite(dts[n])) return fail(ctx, SWMHD_ERR_ARG, "every dt of the sequence must be positive and finite");
+    return step_impl(ctx, 0.0, nsteps, diags, dts);
+}
 extern "C" int swmhd_step_diag(swmhd_ctx *ctx, double dt, int nsteps, swmhd_diag *diags) {
     if (!diags) return ctx ? fail(ctx, SWMHD_ERR_ARG, "diags is null") : SWMHD_ERR_ARG;
     return step_impl(ctx, dt, nsteps, diags);
+}
+
+// set!(model, ...) + time_step!(model, dt) in one call, the upload pipelined with stage 1 by row bands.
+// The four parent arrays travel band by band on the copy stream; as soon as band b and its neighbour band b+1 have
+// arrived and their x halos are wrapped, stage 1 of band b runs on the main stream while later bands are still on the
+// PCIe link.  The first and the last band also need the y halos (periodic images of the other end, or the wall BCs), so
+// they run after the last band has landed.  Stages 2 and 3 follow as usual.  Single slab, between steps.
+extern "C" int swmhd_upload_step(swmhd_ctx *ctx, const double *const host[4], size_t n_each, double dt, swmhd_diag *diag) {
+    if (!ctx || !host) return SWMHD_ERR_ARG;
+    if (multi(ctx)) return fail(ctx, SWMHD_ERR_STATE, "swmhd_upload_step is single-slab (upload with swmhd_set_field, then swmhd_step)");
+    if (ctx->in_substage || ctx->last_stage != 0) return fail(ctx, SWMHD_ERR_STATE, "a step is in flight");
+    if (!(dt > 0.0)) return fail(ctx, SWMHD_ERR_ARG, "dt must be positive");
+    Slab &s = ctx->slabs[0];
+    for (int k = 0; k < 4; k++) {
+        if (!host[k]) return fail(ctx, SWMHD_ERR_ARG, "null host array");
+        if (n_each < s.len[k]) return fail(ctx, SWMHD_ERR_ARG, "n_each is smaller than a field's parent array");
+    }
+    CK(cudaSetDevice(s.dev));
+    const int ty = ctx->ty, ntr = s.ntr, P = ctx->P;
+    // bands of whole tiles: 1/16 of the rows each on large grids (the last band to arrive holds back itself and its two
+    // neighbours: 3/16 of stage 1), 1/8 on small ones, at least two row-blocked tiles
+    const int want = (ntr >= 256) ? 16 : 8;
+    int band_tr = ((ntr + want - 1) / want + ctx->edge_tr - 1) / ctx->edge_tr * ctx->edge_tr;
+    if (band_tr < 2 * ctx->edge_tr) band_tr = 2 * ctx->edge_tr;
+    const int nb = (ntr + band_tr - 1) / band_tr;
+    if (nb < 3) {       // too small to pipeline: plain upload, then a step
+        for (int k = 0; k < 4; k++) CK(cudaMemcpyAsync(s.U[ctx->cur][k], host[k], s.len[k] * sizeof(double), cudaMemcpyHostToDevice, s.main));
+        HaloParams h = halo_params(ctx, s, s.U[ctx->cur], 3, s.Ny + 2, true);
+        ctx->launches++;
+        CK(launch_halo(h, s.main));
+        return step_impl(ctx, dt, 1, diag);
+    }
+    std::vector<cudaEvent_t> ev(nb);
+    for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventRecord(s.ev0, s.main));
+    CK(cudaEventRecord(s.ev_main, s.main));                 // the copy stream may not overwrite what earlier work still reads
+    CK(cudaStreamWaitEvent(s.copy, s.ev_main, 0));
+    auto band_rows = [&](int b, int *r0, int *r1) { *r0 = b * band_tr * ty; *r1 = (b + 1) * band_tr * ty; if (*r1 > s.Ny || b == nb - 1) *r1 = s.Ny; };
+    for (int b = 0; b < nb; b++) {                           // parent rows of band b; the end bands take the halo rows along
+        int r0, r1;
+        band_rows(b, &r0, &r1);
+        for (int k = 0; k < 4; k++) {
+            const size_t lo = (b == 0) ? 0 : (size_t)(3 + r0), hi = (b == nb - 1) ? (size_t)s.rows[k] : (size_t)(3 + r1);
+            CK(cudaMemcpyAsync(s.U[ctx->cur][k] + lo * P, host[k] + lo * P, (hi - lo) * P * sizeof(double), cudaMemcpyHostToDevice, s.copy));
+        }
+        CK(cudaEventRecord(ev[b], s.copy));
+    }
+    KParams p = kparams(ctx, s, dt, 1);
+    if (diag) p.diag = s.d_partials;
+    auto stage1_band = [&](int b) -> int {
+        p.tile_row0 = b * band_tr;
+        p.tile_rows = (b == nb - 1) ? ntr - b * band_tr : band_tr;
+        CK(launch_substage(ctx, p, 1, s.main));
+        return SWMHD_OK;
+    };
+    for (int b = 0; b < nb; b++) {
+        int r0, r1;
+        band_rows(b, &r0, &r1);
+        CK(cudaStreamWaitEvent(s.main, ev[b], 0));
+        HaloParams h = halo_params(ctx, s, s.U[ctx->cur], 3 + r0, 3 + r1 - 1, false);        // x wrap of the band's rows
+        ctx->launches++;
+        CK(launch_halo(h, s.main));
+        if (b >= 2) { int rc = stage1_band(b - 1); if (rc) return rc; }                          // bands b-2, b-1, b are complete
+    }
+    {   // y halos (periodic images / walls), then the two end bands
+        HaloParams h = halo_params(ctx, s, s.U[ctx->cur], 3, 2, true);
+        ctx->launches++;
+        CK(launch_halo(h, s.main));
+        int rc = stage1_band(0);
+        if (rc) return rc;
+        if ((rc = stage1_band(nb - 1))) return rc;
+    }
+    if (diag) {
+        ctx->launches++;
+        CK(launch_diag_final(s.d_partials, s.ntiles, s.d_stage, s.d_diag, s.main));
+    }
+    {
+        HaloParams h = halo_params(ctx, s, s.U[1 - ctx->cur], 3, s.Ny + 2, true);
+        ctx->launches++;
+        CK(launch_halo(h, s.main));
+    }
+    ctx->cur = 1 - ctx->cur;
+    tick(ctx, dt, 1);
+    int rc = substage_async(ctx, dt, 2);
+    if (rc == SWMHD_OK) rc = substage_async(ctx, dt, 3);
+    if (rc == SWMHD_OK && diag) {
+        std::vector<double> r;
+        rc = fetch_diag(ctx, 0, 1, false, r);
+        if (rc == SWMHD_OK) diag_fill(ctx, r.data(), diag);
+    }
+    if (rc == SWMHD_OK) {
+        CK(cudaEventRecord(s.ev1, s.main));
+        rc = sync_all(ctx);
+        float ms = 0;
+        if (rc == SWMHD_OK && cudaEventElapsedTime(&ms, s.ev0, s.ev1) == cudaSuccess) ctx->last_ms = ms;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 // nsteps RK3 steps with a CUDA-event pair around every substage-kernel launch (on the

@@ -265,6 +265,23 @@ def time_step_diag_b(model: ShallowWaterModel, dt, nsteps=1):
     return out
 
 
+def set_and_step_diag_b(model: ShallowWaterModel, dt, **kwargs):
+    """`set!(model, ...)` immediately followed by `time_step!(model, Δt)` with the diagnostics of the uploaded state:
+    all four fields must be given as full parent arrays; the upload is pipelined with stage 1 (swmhd_upload_step)."""
+    by_name = model.fields()
+    if sorted(kwargs) != sorted(by_name):
+        raise ValueError(f"set_and_step_diag_b needs all of {list(by_name)}")
+    U = [None] * 4
+    for name, a in kwargs.items():
+        f = by_name[name]
+        if not (isinstance(a, np.ndarray) and a.shape == f.parent.shape and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+            raise ValueError(f"{name}: C-contiguous float64 parent array of shape {f.parent.shape} expected")
+        U[f.index] = a
+    d = model.ctx.upload_step(U, dt, diag=True)
+    model._mark_stale()
+    return d
+
+
 # -- Simulation -------------------------------------------------------------------------------
 @dataclass
 class IterationInterval:
@@ -341,6 +358,32 @@ class Simulation:
                 dt = min(dt, nt - t)
         return dt
 
+    def _plan_batch(self, max_steps=256):
+        """The Δt sequence up to (and including) the step after which a callback or writer is due, or stop_time /
+        stop_iteration is reached: upstream's aligned_time_step replayed on a copy of the clock, which ticks
+        (8/15, 2/15, 1/3) Δt per RK3 stage exactly like the library's."""
+        g1 = 8.0 / 15.0
+        g2z2 = 5.0 / 12.0 + (-17.0 / 60.0)
+        g3z3 = 3.0 / 4.0 + (-5.0 / 12.0)
+        t, it = self.model.clock.time, self.model.clock.iteration
+        scheds = [c.schedule for c in self.callbacks.values()] + [w.schedule for w in self.output_writers.values()]
+        nexts = [s.next_time(self) for s in scheds if isinstance(s, TimeInterval)]
+        ivals = [s.interval for s in scheds if isinstance(s, IterationInterval)]
+        dts = []
+        while len(dts) < max_steps:
+            dt = min(self.dt, self.stop_time - t)
+            for nt in nexts:
+                if nt > t + 1e-14 * max(1.0, abs(t)):
+                    dt = min(dt, nt - t)
+            dts.append(dt)
+            t = ((t + g1 * dt) + g2z2 * dt) + g3z3 * dt
+            it += 1
+            due_time = any(t >= nt - 1e-12 * max(1.0, abs(nt)) for nt in nexts)
+            due_iter = any(it % iv == 0 for iv in ivals)
+            if due_time or due_iter or t >= self.stop_time - 1e-12 or it >= self.stop_iteration:
+                break
+        return dts
+
     def _fire(self):
         for c in self.callbacks.values():
             if c.schedule.due(self):
@@ -351,26 +394,15 @@ class Simulation:
 
 
 def run_b(sim: Simulation):
-    """`run!(simulation)` (SWMHD_example.jl:97)."""
+    """`run!(simulation)` (SWMHD_example.jl:97): between two events (callback, writer, stop) the whole aligned Δt
+    sequence runs in ONE library call (swmhd_step_seq), the device never returns to the host in between."""
     m = sim.model
     t0 = _time.perf_counter()
     sim._fire()  # iteration 0
-    only_iteration_schedules = all(isinstance(s, IterationInterval) for s in
-                                   [c.schedule for c in sim.callbacks.values()] +
-                                   [w.schedule for w in sim.output_writers.values()])
     while m.clock.time < sim.stop_time - 1e-12 and m.clock.iteration < sim.stop_iteration:
-        dt = sim._aligned_dt()
-        nsteps = 1
-        if only_iteration_schedules:
-            # no event can fall between steps: batch up to the next due iteration
-            ivals = [c.schedule.interval for c in sim.callbacks.values()] + \
-                    [w.schedule.interval for w in sim.output_writers.values()]
-            gap = min([iv - m.clock.iteration % iv for iv in ivals], default=64)
-            left_t = int(max(1, math.floor((sim.stop_time - m.clock.time) / sim.dt + 1e-9))) if math.isfinite(sim.stop_time) else gap
-            left_i = sim.stop_iteration - m.clock.iteration if math.isfinite(sim.stop_iteration) else gap
-            if dt == sim.dt:
-                nsteps = int(max(1, min(gap, left_t, left_i)))
-        time_step_b(m, dt, nsteps)
+        dts = sim._plan_batch()
+        m.ctx.step_seq(dts)
+        m._mark_stale()
         sim._fire()
     sim.run_wall_time = _time.perf_counter() - t0
     return sim

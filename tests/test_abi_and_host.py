@@ -127,3 +127,55 @@ def test_models_validate_reference_options():
                             formulation=M.VectorInvariantFormulation(), **common)
     with pytest.raises(ValueError):
         M.ShallowWaterModel(momentum_advection=M.WENO5(), forcing={}, formulation=M.ConservativeFormulation(), **{**common, "timestepper": "QuasiAdamsBashforth2"})
+
+
+def test_run_plans_the_aligned_dt_sequence_between_events():
+    """run!(simulation) with a TimeInterval(0.1) writer (SWMHD_example.jl:81-84): Simulation._plan_batch replays upstream's
+    aligned_time_step on a copy of the clock, so that every batch of steps between two events is ONE swmhd_step_seq call.
+    Checked against a stand-in context that ticks the clock like the library (no GPU needed)."""
+    from swmhd_b200 import models as M
+
+    class FakeCtx:
+        def __init__(self):
+            self.time, self.iteration, self.calls = 0.0, 0, []
+
+        def step_seq(self, dts, diag=False):
+            self.calls.append(list(dts))
+            for dt in dts:          # tick! per RK3 stage: (8/15, 2/15, 1/3) dt (SURVEY A.7)
+                self.time = ((self.time + (8.0 / 15.0) * dt) + (5.0 / 12.0 - 17.0 / 60.0) * dt) + (3.0 / 4.0 - 5.0 / 12.0) * dt
+                self.iteration += 1
+
+    class FakeModel:
+        def __init__(self):
+            self.ctx = FakeCtx()
+            self.clock = self.ctx
+
+        def _mark_stale(self):
+            pass
+
+    m = FakeModel()
+    sim = M.Simulation(m, dt=0.03, stop_time=0.35)
+    fired = []
+
+    class W:
+        schedule = M.TimeInterval(0.1)
+
+        def write(self, s):
+            fired.append(s.model.clock.time)
+
+    sim.output_writers["fields"] = W()
+    M.run_b(sim)
+    assert np.allclose(fired, [0.0, 0.1, 0.2, 0.3], atol=1e-12)
+    assert abs(m.clock.time - 0.35) < 1e-12
+    # three full steps and the remainder up to each output time, one call per output interval
+    assert [len(c) for c in m.ctx.calls] == [4, 4, 4, 2]
+    for c in m.ctx.calls[:3]:
+        assert np.allclose(c[:3], 0.03) and abs(sum(c) - 0.1) < 1e-12 and 0 < c[3] < 0.03
+    assert np.allclose(m.ctx.calls[3], [0.03, 0.02], atol=1e-12)
+    # iteration schedules batch too: every 5 iterations, stop after 12
+    m2 = FakeModel()
+    sim2 = M.Simulation(m2, dt=0.01, stop_iteration=12)
+    seen = []
+    sim2.callbacks["p"] = M.Callback(lambda s: seen.append(s.model.clock.iteration), M.IterationInterval(5))
+    M.run_b(sim2)
+    assert seen == [0, 5, 10] and [len(c) for c in m2.ctx.calls] == [5, 5, 2]

@@ -187,3 +187,47 @@ def test_context_on_second_device():
     b = run_gpu(cfg1, U, 0.002, 2)
     for k in range(4):
         assert np.array_equal(a[k], b[k])
+
+
+@pytest.mark.parametrize("kind", ["J", "D"])
+def test_step_seq_equals_the_same_steps_one_by_one(kind):
+    """swmhd_step_seq: a batch with a per-step dt (the aligned sequence up to an output time) is bit-identical to the
+    same steps issued one call at a time, clock included; bad sequences are refused before anything runs."""
+    g, cfg, U = make_case(kind, 96, Ny=80, perturb=21)
+    dts = [0.004, 0.004, 0.004, 0.0013, 0.004, 0.0007]
+    a = Context(cfg); a.set_state(U); a.fill_halos()
+    for dt in dts:
+        a.step(dt, 1)
+    Ua, ta, ia = a.get_state(), a.time, a.iteration
+    da = a.diagnostics(); a.close()
+    b = Context(cfg); b.set_state(U); b.fill_halos()
+    tr = b.step_seq(dts, diag=True)
+    Ub, tb, ib = b.get_state(), b.time, b.iteration
+    with pytest.raises(SwmhdError) as e:
+        b.step_seq([0.004, 0.0, 0.004])
+    assert e.value.code == abi.ERR_ARG and b.iteration == ib
+    b.close()
+    assert ta == tb and ia == ib == len(dts) and len(tr) == len(dts)
+    for k in range(4):
+        assert np.array_equal(Ua[k], Ub[k])
+
+
+@pytest.mark.parametrize("kind,N,Ny", [("J", 256, 1024), ("D", 248, 776), ("BJ", 128, 520), ("BD", 128, 512), ("J", 96, 80)])
+def test_upload_step_equals_set_then_step(kind, N, Ny):
+    """swmhd_upload_step (set! + time_step!, the upload pipelined with stage 1 by row bands) is bit-identical to
+    set_field x 4 + fill_halos + step_diag(1) — halos of the host arrays need not be filled — and leaves the clock alike."""
+    g, cfg, U = make_case(kind, N, Ny=Ny, perturb=41)
+    a = Context(cfg); a.set_state(U); a.fill_halos(); da = a.step_diag(0.002, 1)[0]; a.step(0.002, 1)
+    Ua, ta = a.get_state(), a.time; a.close()
+    pinned = [torch.from_numpy(u.copy()).pin_memory().numpy() for u in U]
+    b = Context(cfg)
+    db = b.upload_step(pinned, 0.002, diag=True); b.step(0.002, 1)
+    Ub, tb = b.get_state(), b.time
+    db2 = b.upload_step(pinned, 0.002, diag=True)        # again, from a context that has history
+    b.close()
+    assert ta == tb
+    for k in range(4):
+        assert np.array_equal(Ua[k], Ub[k]), k
+    for key in ("ke", "me", "pe", "sum_h", "max_abs_u", "max_abs_A", "min_h", "max_abs_div_hB"):
+        assert abs(da[key] - db[key]) <= 1e-13 * max(1.0, abs(da[key])), key
+        assert db2[key] == db[key], key
