@@ -33,8 +33,37 @@ function build(form, N)
     return model
 end
 
+# Bounded-y with activity AT the walls (pins Appendix-C item C10: halo depth of the no-flux / gradient BCs, the WENO wall
+# fallback, v beyond the wall — the published Bounded-y figures cannot, their wall region is quiescent, profiles/r02_c10_probe.md).
+# A = -0.05 y + 0.02 exp(-(x^2 + (y-4)^2)) with GradientBoundaryCondition(-0.05) (divergence_sw_mhd.jl:17), vortex centred at (0, 3.5).
+function build_wall(form, N)
+    grid = RectilinearGrid(size = (N, N), x = (-5, 5), y = (-5, 5), topology = (Periodic, Bounded, Flat))
+    A_bcs = FieldBoundaryConditions(north = GradientBoundaryCondition(-0.05), south = GradientBoundaryCondition(-0.05))
+    Ai(x, y, z) = -0.05y + 0.02exp(-(x^2 + (y - 4)^2))
+    ui(x, y, z) = (y - 3.5) * exp(-(x^2 + (y - 3.5)^2))
+    vi(x, y, z) = -x * exp(-(x^2 + (y - 3.5)^2))
+    if form == :jacobian_wall
+        include(joinpath(refroot, "jacobian_formulation", "sw_mhd_jacobian_functions.jl"))
+        model = ShallowWaterModel(grid = grid, timestepper = :RungeKutta3, boundary_conditions = (A = A_bcs,),
+            momentum_advection = WENO5(vector_invariant = VelocityStencil()), mass_advection = WENO5(), tracer_advection = WENO5(),
+            gravitational_acceleration = 9.81, coriolis = FPlane(f = 1), tracers = (:A),
+            forcing = (u = Forcing(lorentz_force_func_x, discrete_form = true), v = Forcing(lorentz_force_func_y, discrete_form = true)),
+            formulation = VectorInvariantFormulation())
+        set!(model, u = ui, v = vi, h = 1, A = Ai)
+    else
+        include(joinpath(refroot, "divergence_formulation", "sw_mhd_divergence_functions.jl"))
+        model = ShallowWaterModel(grid = grid, timestepper = :RungeKutta3, boundary_conditions = (A = A_bcs,),
+            momentum_advection = WENO5(), mass_advection = WENO5(), tracer_advection = WENO5(),
+            gravitational_acceleration = 9.81, coriolis = FPlane(f = 1), tracers = (:A),
+            forcing = (uh = Forcing(div_lorentz_x, discrete_form = true), vh = Forcing(div_lorentz_y, discrete_form = true)),
+            formulation = ConservativeFormulation())
+        set!(model, uh = ui, vh = vi, h = 1, A = Ai)
+    end
+    return model
+end
+
 function dump(model, form, N, k, outdir)
-    names = form == :jacobian ? (:u, :v, :h) : (:uh, :vh, :h)
+    names = form in (:jacobian, :jacobian_wall) ? (:u, :v, :h) : (:uh, :vh, :h)
     fields = (getproperty(model.solution, names[1]), getproperty(model.solution, names[2]), model.solution.h, model.tracers.A)
     for (f, tag) in zip(fields, ("u", "v", "h", "A"))
         write(joinpath(outdir, "golden_$(form)_$(N)_step$(k)_$(tag).f64"), Array(parent(f)))
@@ -49,6 +78,19 @@ for form in (:jacobian, :divergence), N in (64,)
     dump(model, form, N, 0, outdir)
     n = 0
     for k in (1, 10, 100, 1000)
+        for _ in 1:(k - n)
+            time_step!(model, 0.01)
+        end
+        n = k
+        dump(model, form, N, k, outdir)
+    end
+end
+for form in (:jacobian_wall, :divergence_wall), N in (64,)
+    model = build_wall(form, N)
+    Oceananigans.TimeSteppers.update_state!(model)
+    dump(model, form, N, 0, outdir)          # step 0 already shows which halo cells upstream fills
+    n = 0
+    for k in (1, 10, 100)
         for _ in 1:(k - n)
             time_step!(model, 0.01)
         end
