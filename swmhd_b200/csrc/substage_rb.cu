@@ -52,7 +52,10 @@ static_assert((R & (R - 1)) == 0 && 2 * R <= 32, "rows per warp: power of two");
 constexpr int W = TX + 6, HT = TYB + 6, SZ = W * HT;       // raw tiles: [HT][W] (dense TMA box)
 constexpr int SZP = (SZ * 8 + 127) / 128 * 16;             // padded to a multiple of 128 B (TMA dst alignment)
 constexpr unsigned TILE_TX_BYTES = 4u * SZ * 8u;
-constexpr int ZP = TX + 5, ZR = TYB + 5;                   // ffc points a in [1,TX+5], b in [1,TYB+5]
+// ffc points a in [1,TX+5], b in [1,TYB+5], stored with the pitch of the raw tile (one unused column): point q of the
+// array is raw index q + W + 1, so phase A walks both with one counter, and a warp's 32 consecutive points never
+// straddle a hole (the row wrap of a 37-wide array cost an extra shared-memory wavefront per straddling half-warp)
+constexpr int ZP = TX + 6, ZR = TYB + 5;
 constexpr int CP = TX + 2, CR = TYB + 2;                   // ccc points a in [2,TX+3], b in [2,TYB+3]
 constexpr int NZ = ZP * ZR, NC = CP * CR;
 constexpr int o_z = 0, o_ut = NZ, o_vt = 2 * NZ, o_Bx = 3 * NZ, o_By = o_Bx + NC;
@@ -62,6 +65,7 @@ constexpr int DERIVED = o_By + NC;
 constexpr int NE = 4 * R + 2;
 static_assert(NE >= NDIAG, "the per-warp scratch also holds the warp's diagnostic partials");
 constexpr size_t SMEM_BYTES = ((size_t)4 * SZP + DERIVED + 2 + NW * NE) * sizeof(double);   // + mbarrier + per-warp scratch
+static_assert(RB_MINB * (SMEM_BYTES + 1024) <= 228 * 1024, "Jacobian kernel: shared memory of RB_MINB CTAs per SM (1 KB reserved per CTA)");
 
 #define RAW(arr, a, b) arr[(b) * W + (a)]
 #define Zf(arr, a, b) arr[((b) - 1) * ZP + (a) - 1]
@@ -151,18 +155,14 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
     mbar_wait(mbar, 0);
 
     // ---- A: derived staggered fields, each point once per tile --------------------------------------
-    {   // zeta, ℑy u, ℑx v at ffc: point q = (a, b) of the ZP-wide array, raw index r; both advanced incrementally
-        constexpr int DA = NT % ZP, DB = NT / ZP;
-        int a = tid % ZP, r = (tid / ZP + 1) * W + a + 1;
+    static_assert(ZP == W, "derived ffc arrays share the pitch of the raw tile");
 #pragma unroll 4
-        for (int q = tid; q < NZ; q += NT) {
-            const double vc = s_v[r], vw = s_v[r - 1], uc = s_u[r], us = s_u[r - W];
-            s_z[q] = fma(vc - vw, p.rdx, (us - uc) * p.rdy);
-            s_ut[q] = 0.5 * (us + uc);
-            s_vt[q] = 0.5 * (vw + vc);
-            a += DA; r += DB * W + DA;
-            if (a >= ZP) { a -= ZP; r += W - ZP; }
-        }
+    for (int q = tid; q < NZ; q += NT) {                    // zeta, ℑy u, ℑx v at ffc; raw index of point q is q + W + 1
+        const int r = q + W + 1;
+        const double vc = s_v[r], vw = s_v[r - 1], uc = s_u[r], us = s_u[r - W];
+        s_z[q] = fma(vc - vw, p.rdx, (us - uc) * p.rdy);
+        s_ut[q] = 0.5 * (us + uc);
+        s_vt[q] = 0.5 * (vw + vc);
     }
     {   // Bx, By at ccc (sw_mhd_jacobian_functions.jl:1-7)
         constexpr int DA = NT % CP, DB = NT / CP;
@@ -478,11 +478,14 @@ __global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_c
 // a tile is 31 cells wide (32 faces), which costs 3 % of the lanes instead of a pre-pass over three
 // flux families.
 constexpr int TXD = TX - 1;                                // cells per tile row in the divergence kernel
-constexpr int BP = TX + 4, BR = TYB + 4;                   // hBx, hBy, Bx, By: a in [1,TX+4], b in [1,TYB+4]
-constexpr int RP = TX + 2, RR = TYB + 2;                   // 1/h at ccc: a in [2,TX+3], b in [2,TYB+3]
+// hBx, hBy, Bx, By: a in [1,TX+4], b in [1,TYB+4]; 1/h at ccc: a in [2,TX+3], b in [2,TYB+3].  All at the pitch of the raw
+// tile (unused columns at the end of each row): point t of an array is raw index t + const, no holes inside a warp's 32 points
+constexpr int BP = TX + 6, BR = TYB + 4;
+constexpr int RP = TX + 6, RR = TYB + 2;
 constexpr int NB = BP * BR, NRH = RP * RR;
 constexpr int DERIVED_D = 4 * NB + NRH;                    // 55.4 KB with the raw tile: 4 CTAs per SM
 constexpr size_t SMEM_BYTES_D = ((size_t)4 * SZP + DERIVED_D + 2 + NW * NDIAG) * sizeof(double);
+static_assert(RB_MINB_D * (SMEM_BYTES_D + 1024) <= 228 * 1024, "divergence kernel: shared memory of RB_MINB_D CTAs per SM (1 KB reserved per CTA)");
 #define Bf(arr, a, b) arr[((b) - 1) * BP + (a) - 1]
 #define RH(a, b) s_rh[((b) - 2) * RP + (a) - 2]
 
@@ -548,12 +551,12 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
     mbar_wait(mbar, 0);
 
     // ---- A: hBx, hBy, Bx, By (sw_mhd_divergence_functions.jl:134-148) and the reciprocal depths ---------
-    {   // point t = (a, b) of the BP-wide arrays, raw index r; both advanced incrementally
-        constexpr int DA = NT % BP, DB = NT / BP;
-        int a = tid % BP, r = (tid / BP + 1) * W + a + 1;
+    static_assert(BP == W && RP == W, "derived arrays share the pitch of the raw tile");
+    {
         const double qy = 0.25 * p.rdy, qx = 0.25 * p.rdx;
 #pragma unroll 2
-        for (int t = tid; t < NB; t += NT) {
+        for (int t = tid; t < NB; t += NT) {                // raw index of point t is t + W + 1
+            const int r = t + W + 1;
             // telescoped ℑxy∂: hBx = -(ℑxy ∂y A), hBy = ℑxy ∂x A
             const double Asw = s_A[r - W - 1], As = s_A[r - W], Aw = s_A[r - 1];
             const double hbx = ((Asw + As) - (s_A[r + W - 1] + s_A[r + W])) * qy;
@@ -563,19 +566,9 @@ __global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __gri
             rcp_n<2>(x2, r2);
             s_hBx[t] = hbx; s_hBy[t] = hby;
             s_Bx[t] = hbx * r2[0]; s_By[t] = hby * r2[1];
-            a += DA; r += DB * W + DA;
-            if (a >= BP) { a -= BP; r += W - BP; }
         }
     }
-    {
-        constexpr int DA = NT % RP, DB = NT / RP;
-        int a = tid % RP, r = (tid / RP + 2) * W + a + 2;
-        for (int q = tid; q < NRH; q += NT) {
-            s_rh[q] = frcp(s_h[r]);
-            a += DA; r += DB * W + DA;
-            if (a >= RP) { a -= RP; r += W - RP; }
-        }
-    }
+    for (int q = tid; q < NRH; q += NT) s_rh[q] = frcp(s_h[q + 2 * W + 2]);     // raw index of point q is q + 2 W + 2
     __syncthreads();
 
     // ---- B/C: warp-private row walk ----------------------------------------------------------------------

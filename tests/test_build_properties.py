@@ -38,8 +38,8 @@ def test_shared_memory_layout_fits_four_ctas_per_sm():
     TX, TYB, R = 32, macro("RB_TY"), macro("RB_R")
     NW, NDIAG = TYB // R, 9
     SZP = ((TX + 6) * (TYB + 6) * 8 + 127) // 128 * 16
-    jac = 4 * SZP + 3 * (TX + 5) * (TYB + 5) + 2 * (TX + 2) * (TYB + 2) + 2 + NW * (4 * R + 2)    # per-warp east-column scratch
-    div = 4 * SZP + 4 * (TX + 4) * (TYB + 4) + (TX + 2) * (TYB + 2) + 2 + NW * NDIAG
+    jac = 4 * SZP + 3 * (TX + 6) * (TYB + 5) + 2 * (TX + 2) * (TYB + 2) + 2 + NW * (4 * R + 2)    # ffc arrays at the raw pitch; per-warp east-column scratch
+    div = 4 * SZP + 4 * (TX + 6) * (TYB + 4) + (TX + 6) * (TYB + 2) + 2 + NW * NDIAG          # derived arrays at the raw pitch
     assert "constexpr int DERIVED = o_By + NC;" in SRC and "constexpr int DERIVED_D = 4 * NB + NRH;" in SRC
     budget = (228 * 1024 - 4 * 1024) // 4           # 228 KB per SM, 1 KB reserved per resident CTA
     assert jac * 8 <= budget and div * 8 <= budget, (jac * 8, div * 8, budget)
