@@ -231,3 +231,19 @@ def test_upload_step_equals_set_then_step(kind, N, Ny):
     for key in ("ke", "me", "pe", "sum_h", "max_abs_u", "max_abs_A", "min_h", "max_abs_div_hB"):
         assert abs(da[key] - db[key]) <= 1e-13 * max(1.0, abs(da[key])), key
         assert db2[key] == db[key], key
+
+
+@pytest.mark.parametrize("kind", ["J", "D", "BJ"])
+def test_fast_1000_steps_at_256(kind):
+    """north_star: rel-L2 <= 1e-9 per field after 1000 steps, here at 256^2 (16x the cells of the 64^2 case of
+    test_gpu_parity.py::test_fast_1000_steps), periodic and Bounded-y."""
+    N = 256
+    g, cfg, U = make_case(kind, N, arith=abi.ARITH_FAST)
+    dt = 0.01 * 64 / N
+    Ug = run_gpu(cfg, U, dt, 1000)
+    O.set_threads(64)
+    O.fill_halos(cfg, U)
+    O.step(cfg, U, dt, 1000)
+    for k in range(4):
+        err = rel_l2(g, Ug[k], U[k], k)
+        assert err <= 1e-9, f"field {k}: rel L2 {err:.3e}"
