@@ -227,6 +227,9 @@ int  swmhd_substage_finish(swmhd_ctx *ctx, int stage);              /* swap buff
 int  swmhd_exchange_rows(swmhd_ctx *ctx, int field, int which,
                          void **dev_ptr, int *nrows, size_t *row_doubles);
 int  swmhd_sync(swmhd_ctx *ctx);
+/* Test hook for pools without compute-sanitizer: with SWMHD_GUARD=1 in the environment at swmhd_create every device array
+   sits between two 32 KB guard zones filled with a sentinel; SWMHD_OK = no kernel wrote outside its arrays so far. */
+int  swmhd_check_guards(swmhd_ctx *ctx);
 /* Slab diagnostics without a host round trip per step: arm a slot (0..1023) and the next stage-1
    substage (edges + interior) also evaluates the diagnostics of the state it starts from, fused in
    the substage kernels; read any number of slots later.  Values are slab partials scaled by the

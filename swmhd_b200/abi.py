@@ -122,6 +122,7 @@ SYMBOLS = [
     ("swmhd_exchange_rows", C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                       C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
     ("swmhd_sync", C.c_int, [_ctx]),
+    ("swmhd_check_guards", C.c_int, [_ctx]),
     ("swmhd_arm_diag", C.c_int, [_ctx, C.c_int]),
     ("swmhd_get_diag_slots", C.c_int, [_ctx, C.c_int, C.c_int, C.POINTER(Diag)]),
     ("swmhd_step_profile", C.c_int, [_ctx, C.c_double, C.c_int, C.POINTER(C.c_double)]),

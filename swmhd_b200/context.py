@@ -193,6 +193,10 @@ class Context:
         self._ck(self.lib.swmhd_get_diag_slots(self._h, int(first), int(count), arr))
         return [d.as_dict() for d in arr]
 
+    def check_guards(self):
+        """SWMHD_GUARD=1 contexts: raise if any kernel wrote outside its device arrays."""
+        self._ck(self.lib.swmhd_check_guards(self._h))
+
     def sync(self):
         self._ck(self.lib.swmhd_sync(self._h))
 

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 using namespace swmhd;
@@ -43,6 +44,10 @@ struct Slab {
     ncclComm_t comm = nullptr;
     int pending_slot = -1;
     bool out_in_flight = false;
+    // SWMHD_GUARD=1 (test hook: compute-sanitizer is not available on every pool): every device array sits between two
+    // guard zones filled with a sentinel; swmhd_check_guards verifies that no kernel wrote outside its arrays
+    std::vector<std::pair<double *, size_t>> guarded;     // (user pointer, user doubles) of every guarded allocation
+    bool guard = false;                                   // decided once, at create
 };
 
 } // namespace
@@ -139,6 +144,28 @@ extern "C" int swmhd_split_rows(int Ny, int nslabs, int index, int *j0, int *ny)
 
 static bool multi(const swmhd_ctx *ctx) { return ctx->nslabs_total > 1; }
 
+// ---- guarded allocations (SWMHD_GUARD) -----------------------------------------------------------------------
+constexpr size_t GUARD_DOUBLES = 4096;                     // 32 KB on each side: keeps the 16-byte alignment TMA needs
+static const unsigned long long GUARD_WORD = 0x7ff8dead7ff8beefull;   // a quiet NaN with a recognisable payload
+static bool guard_on() { const char *e = getenv("SWMHD_GUARD"); return e && *e && *e != '0'; }
+
+static cudaError_t dev_alloc(Slab &s, double **out, size_t n) {
+    if (!s.guard) return cudaMalloc(out, n * sizeof(double));
+    double *base = nullptr;
+    cudaError_t e = cudaMalloc(&base, (n + 2 * GUARD_DOUBLES) * sizeof(double));
+    if (e != cudaSuccess) return e;
+    std::vector<unsigned long long> g(GUARD_DOUBLES, GUARD_WORD);
+    if ((e = cudaMemcpy(base, g.data(), GUARD_DOUBLES * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    if ((e = cudaMemcpy(base + GUARD_DOUBLES + n, g.data(), GUARD_DOUBLES * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+    *out = base + GUARD_DOUBLES;
+    s.guarded.emplace_back(*out, n);
+    return cudaSuccess;
+}
+static void dev_free(const Slab &s, double *p) {
+    if (!p) return;
+    cudaFree(s.guard ? p - GUARD_DOUBLES : p);
+}
+
 // ---------------------------------------------------------------------------
 static int create_slab(swmhd_ctx *ctx, Slab &s, std::string &why) {
     const swmhd_config &c = ctx->cfg;
@@ -150,6 +177,7 @@ static int create_slab(swmhd_ctx *ctx, Slab &s, std::string &why) {
         return SWMHD_ERR_CUDA;
     };
     if ((e = cudaSetDevice(s.dev)) != cudaSuccess) return bad("cudaSetDevice", e);
+    s.guard = guard_on();
     for (int k = 0; k < 4; k++) {
         s.rows[k] = s.Ny + 6 + ((k == SWMHD_V && c.topo_y == SWMHD_BOUNDED) ? 1 : 0);
         s.len[k] = (size_t)ctx->P * s.rows[k];
@@ -165,10 +193,10 @@ static int create_slab(swmhd_ctx *ctx, Slab &s, std::string &why) {
     for (int k = 0; k < 4; k++) {
         const size_t bytes = s.len[k] * sizeof(double);
         for (int b = 0; b < 2; b++) {
-            if ((e = cudaMalloc(&s.U[b][k], bytes)) != cudaSuccess) return bad("cudaMalloc state", e);
+            if ((e = dev_alloc(s, &s.U[b][k], s.len[k])) != cudaSuccess) return bad("cudaMalloc state", e);
             if ((e = cudaMemset(s.U[b][k], 0, bytes)) != cudaSuccess) return bad("cudaMemset", e);
         }
-        if ((e = cudaMalloc(&s.G[k], bytes)) != cudaSuccess) return bad("cudaMalloc tendency", e);
+        if ((e = dev_alloc(s, &s.G[k], s.len[k])) != cudaSuccess) return bad("cudaMalloc tendency", e);
         if ((e = cudaMemset(s.G[k], 0, bytes)) != cudaSuccess) return bad("cudaMemset", e);
     }
     for (int b = 0; b < 2 && ctx->use_tma; b++)
@@ -188,11 +216,11 @@ static int create_slab(swmhd_ctx *ctx, Slab &s, std::string &why) {
     s.nblocks_diag = diag_blocks(ctx->Nx, s.Ny);
     s.ntiles = diag_tiles_x * s.ntr;
     if (s.ntiles > s.nblocks_diag) s.nblocks_diag = s.ntiles;   // d_partials serves both diag paths
-    if ((e = cudaMalloc(&s.d_partials, (size_t)s.nblocks_diag * NDIAG * sizeof(double))) != cudaSuccess) return bad("cudaMalloc diag", e);
-    if ((e = cudaMalloc(&s.d_diag, (size_t)ctx->diag_slots * NDIAG * sizeof(double))) != cudaSuccess) return bad("cudaMalloc diag", e);
-    if ((e = cudaMalloc(&s.d_stage, (size_t)diag_stage_doubles() * sizeof(double))) != cudaSuccess) return bad("cudaMalloc diag", e);
+    if ((e = dev_alloc(s, &s.d_partials, (size_t)s.nblocks_diag * NDIAG)) != cudaSuccess) return bad("cudaMalloc diag", e);
+    if ((e = dev_alloc(s, &s.d_diag, (size_t)ctx->diag_slots * NDIAG)) != cudaSuccess) return bad("cudaMalloc diag", e);
+    if ((e = dev_alloc(s, &s.d_stage, (size_t)diag_stage_doubles())) != cudaSuccess) return bad("cudaMalloc diag", e);
     if ((e = cudaMemset(s.d_stage, 0, (size_t)diag_stage_doubles() * sizeof(double))) != cudaSuccess) return bad("cudaMemset", e);   // ticket word = 0
-    if ((e = cudaMalloc(&s.d_red, (size_t)2 * ctx->diag_slots * NDIAG * sizeof(double))) != cudaSuccess) return bad("cudaMalloc diag", e);
+    if ((e = dev_alloc(s, &s.d_red, (size_t)2 * ctx->diag_slots * NDIAG)) != cudaSuccess) return bad("cudaMalloc diag", e);
     int lo, hi;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if ((e = cudaStreamCreateWithPriority(&s.main, cudaStreamNonBlocking, lo)) != cudaSuccess) return bad("stream", e);
@@ -304,9 +332,9 @@ extern "C" void swmhd_destroy(swmhd_ctx *ctx) {
         cudaDeviceSynchronize();
         if (s.comm && nccl_api()) nccl_api()->CommDestroy(s.comm);
         for (int k = 0; k < 4; k++) {
-            cudaFree(s.U[0][k]); cudaFree(s.U[1][k]); cudaFree(s.G[k]); cudaFree(s.O[k]);
+            dev_free(s, s.U[0][k]); dev_free(s, s.U[1][k]); dev_free(s, s.G[k]); dev_free(s, s.O[k]);
         }
-        cudaFree(s.d_partials); cudaFree(s.d_diag); cudaFree(s.d_stage); cudaFree(s.d_red);
+        dev_free(s, s.d_partials); dev_free(s, s.d_diag); dev_free(s, s.d_stage); dev_free(s, s.d_red);
         if (s.own_streams) {
             if (s.main) cudaStreamDestroy(s.main);
             if (s.edge) cudaStreamDestroy(s.edge);
@@ -979,7 +1007,7 @@ extern "C" int swmhd_get_outputs_async(swmhd_ctx *ctx, double *u_host, double *v
         CK(cudaSetDevice(s.dev));
         const int shape[4] = {SWMHD_U, SWMHD_V, SWMHD_U, SWMHD_A};
         for (int k = 0; k < 4; k++)
-            if (!s.O[k]) CK(cudaMalloc(&s.O[k], s.len[shape[k]] * sizeof(double)));
+            if (!s.O[k]) CK(dev_alloc(s, &s.O[k], s.len[shape[k]]));
         // the staging buffers may still be read by the previous asynchronous copy
         if (s.out_in_flight) CK(cudaStreamWaitEvent(s.main, s.ev_out_done, 0));
     }
@@ -1121,6 +1149,35 @@ extern "C" int swmhd_get_diag_slots(swmhd_ctx *ctx, int first, int count, swmhd_
     rc = fetch_diag(ctx, first, count, false, host);     // this process's slabs only: the host combines ranks
     if (rc) return rc;
     for (int n = 0; n < count; n++) diag_fill(ctx, &host[(size_t)n * NDIAG], &out[n]);
+    return SWMHD_OK;
+}
+
+// Test hook (SWMHD_GUARD=1 at create time): SWMHD_OK when every guard zone still holds its sentinel, SWMHD_ERR_STATE and a
+// message naming the first damaged allocation otherwise; SWMHD_ERR_ARG when the context was created without guards.
+extern "C" int swmhd_check_guards(swmhd_ctx *ctx) {
+    if (!ctx) return SWMHD_ERR_ARG;
+    int rc = sync_all(ctx);
+    if (rc) return rc;
+    std::vector<unsigned long long> g(GUARD_DOUBLES);
+    size_t checked = 0;
+    for (auto &s : ctx->slabs) {
+        CK(cudaSetDevice(s.dev));
+        for (size_t a = 0; a < s.guarded.size(); a++) {
+            for (int side = 0; side < 2; side++) {
+                const double *z = side ? s.guarded[a].first + s.guarded[a].second : s.guarded[a].first - GUARD_DOUBLES;
+                CK(cudaMemcpy(g.data(), z, GUARD_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost));
+                for (size_t t = 0; t < GUARD_DOUBLES; t++)
+                    if (g[t] != GUARD_WORD) {
+                        char buf[200];
+                        snprintf(buf, sizeof buf, "guard zone %s allocation %zu (slab %d, %zu doubles) overwritten at offset %zu",
+                                 side ? "after" : "before", a, s.index, s.guarded[a].second, t);
+                        return fail(ctx, SWMHD_ERR_STATE, buf);
+                    }
+                checked++;
+            }
+        }
+    }
+    if (!checked) return fail(ctx, SWMHD_ERR_ARG, "context was created without SWMHD_GUARD=1");
     return SWMHD_OK;
 }
 

@@ -247,3 +247,31 @@ def test_fast_1000_steps_at_256(kind):
     for k in range(4):
         err = rel_l2(g, Ug[k], U[k], k)
         assert err <= 1e-9, f"field {k}: rel L2 {err:.3e}"
+
+
+def test_no_kernel_writes_outside_its_arrays(monkeypatch):
+    """compute-sanitizer is closed on this pool: with SWMHD_GUARD=1 every device array sits between two 32 KB guard zones;
+    after stepping ragged, odd, tiny, wide and Bounded-y grids through every kernel route (row-blocked, one thread per cell,
+    fused diagnostics, tendencies, outputs, upload pipeline) all sentinels must be intact."""
+    monkeypatch.setenv("SWMHD_GUARD", "1")
+    rng = np.random.default_rng(7)
+    cases = [("J", 8, 8), ("D", 8, 9), ("BJ", 10, 12), ("BD", 34, 9), ("J", 70, 50), ("D", 65, 43), ("BJ", 64, 40), ("BD", 96, 80),
+             ("J", 130, 33), ("D", 250, 264), ("J", 256, 1024), ("BD", 128, 520)]
+    for _ in range(6):
+        cases.append((["J", "D", "BJ", "BD"][int(rng.integers(4))], int(rng.integers(8, 200)), int(rng.integers(8, 300))))
+    for kind, N, Ny in cases:
+        for arith in (abi.ARITH_FAST, abi.ARITH_STRICT):
+            g, cfg, U = make_case(kind, N, Ny=Ny, arith=arith, perturb=3)
+            c = Context(cfg); c.set_state(U); c.fill_halos()
+            c.step(0.002, 2); c.step_diag(0.002, 2); c.tendencies(); c.get_outputs(); c.diagnostics()
+            c.upload_step(U, 0.002, diag=True)
+            bufs = [np.zeros(c.field_shape(k)) for k in (abi.U, abi.V, abi.U, abi.A)]
+            c.get_outputs_async(*bufs); c.outputs_wait()
+            c.check_guards()
+            c.close()
+    monkeypatch.delenv("SWMHD_GUARD")
+    g, cfg, U = make_case("J", 32, Ny=16)
+    c = Context(cfg)
+    with pytest.raises(SwmhdError):
+        c.check_guards()                      # created without guards: says so instead of reporting a clean bill
+    c.close()
