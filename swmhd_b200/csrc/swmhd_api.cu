@@ -123,6 +123,21 @@ static bool encode_field_map(CUtensorMap *tm, double *base, int P, int rows, int
         }                                                                                     \
     } while (0)
 
+// a batch of CUDA events that is destroyed on every exit path of the function that owns it
+struct EventBatch {
+    std::vector<cudaEvent_t> ev;
+    cudaError_t create(size_t n, unsigned flags) {
+        ev.assign(n, nullptr);
+        for (auto &e : ev) {
+            cudaError_t rc = cudaEventCreateWithFlags(&e, flags);
+            if (rc != cudaSuccess) return rc;
+        }
+        return cudaSuccess;
+    }
+    cudaEvent_t operator[](size_t i) const { return ev[i]; }
+    ~EventBatch() { for (auto e : ev) if (e) cudaEventDestroy(e); }
+};
+
 static int fail(swmhd_ctx *ctx, int code, const char *msg) {
     if (ctx) ctx->err = msg; else g_create_err = msg;
     return code;
@@ -827,8 +842,8 @@ extern "C" int swmhd_upload_step(swmhd_ctx *ctx, const double *const host[4], si
         CK(launch_halo(h, s.main));
         return step_impl(ctx, dt, 1, diag);
     }
-    std::vector<cudaEvent_t> ev(nb);
-    for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    EventBatch ev;
+    CK(ev.create(nb, cudaEventDisableTiming));
     CK(cudaEventRecord(s.ev0, s.main));
     CK(cudaEventRecord(s.ev_main, s.main));                 // the copy stream may not overwrite what earlier work still reads
     CK(cudaStreamWaitEvent(s.copy, s.ev_main, 0));
@@ -891,7 +906,6 @@ extern "C" int swmhd_upload_step(swmhd_ctx *ctx, const double *const host[4], si
         float ms = 0;
         if (rc == SWMHD_OK && cudaEventElapsedTime(&ms, s.ev0, s.ev1) == cudaSuccess) ctx->last_ms = ms;
     }
-    for (auto &e : ev) cudaEventDestroy(e);
     return rc;
 }
 
@@ -904,8 +918,8 @@ static int step_profile_impl(swmhd_ctx *ctx, double dt, int nsteps, double out_m
     if (ctx->last_stage != 0 || ctx->in_substage) return fail(ctx, SWMHD_ERR_STATE, "a step is in flight");
     Slab &s = ctx->slabs[0];
     CK(cudaSetDevice(s.dev));
-    std::vector<cudaEvent_t> ev((size_t)nsteps * 6);
-    for (auto &e : ev) CK(cudaEventCreate(&e));
+    EventBatch ev;
+    CK(ev.create((size_t)nsteps * 6, cudaEventDefault));
     int rc = SWMHD_OK;
     for (int n = 0; n < nsteps && rc == SWMHD_OK; n++)
         for (int st = 1; st <= 3 && rc == SWMHD_OK; st++)
@@ -922,7 +936,6 @@ static int step_profile_impl(swmhd_ctx *ctx, double dt, int nsteps, double out_m
             out_ms[st] = acc / nsteps;
         }
     }
-    for (auto &e : ev) cudaEventDestroy(e);
     return rc;
 }
 extern "C" int swmhd_step_profile(swmhd_ctx *ctx, double dt, int nsteps, double out_ms[3]) { return step_profile_impl(ctx, dt, nsteps, out_ms, false); }
