@@ -43,6 +43,13 @@ namespace {
 #ifndef RB_MINB_D          // the divergence kernel: 55.4 KB of shared memory
 #define RB_MINB_D 4
 #endif
+// Register cap of the variants WITHOUT fused diagnostics: compiled for 3 CTAs/SM (<= 168 registers) ptxas still ends at
+// 114-126 registers — 4 CTAs/SM stay resident (tests/test_build_properties.py checks <= 128) — but schedules with less
+// rematerialisation: 1.909 vs 1.940 ms (Jacobian), 2.014 vs 2.037 ms (divergence) per step at 4096^2.  The DIAG variants
+// need the cap of 4 (they would take 142-152 registers and lose the fourth CTA).
+#ifndef RB_MINB_PLAIN
+#define RB_MINB_PLAIN 3
+#endif
 #ifndef RB_L2_PREFETCH
 #define RB_L2_PREFETCH 1
 #endif
@@ -106,7 +113,7 @@ __device__ __forceinline__ void diffs_mem(const double *q, int s, double &d1, do
 
 // STAGE 1,2,3.  DIAG only with STAGE 1.
 template <int STAGE, bool DIAG>
-__global__ void __launch_bounds__(NT, RB_MINB) substage_rb_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(NT, DIAG ? RB_MINB : RB_MINB_PLAIN) substage_rb_kernel(const __grid_constant__ KParams p) {
     // 128-byte aligned for the TMA destination; used directly so that the compiler keeps the shared
     // address space (LDS/STS instead of generic LD/ST).
     extern __shared__ __align__(128) unsigned char smem_bytes[];
@@ -502,7 +509,7 @@ __device__ __forceinline__ double thirdR(double xm, double x5, double x2) {     
 __device__ __forceinline__ double upwind_sel(double vel, double L, double Rr) { return vel * (vel > 0.0 ? L : Rr); }
 
 template <int STAGE, bool DIAG>
-__global__ void __launch_bounds__(NT, RB_MINB_D) substage_rbd_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(NT, DIAG ? RB_MINB_D : RB_MINB_PLAIN) substage_rbd_kernel(const __grid_constant__ KParams p) {
     extern __shared__ __align__(128) unsigned char smem_bytes[];
     double *const s_u = reinterpret_cast<double *>(smem_bytes);
     double *const s_v = s_u + SZP, *const s_h = s_u + 2 * SZP, *const s_A = s_u + 3 * SZP;
