@@ -17,8 +17,6 @@ combined with one small all_reduce.
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
-
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -114,11 +112,6 @@ def run_in_step_for(seconds: float, step, device, clock=None) -> int:
         go.fill_(1 if clock() - t_s < seconds else 0)
         dist.broadcast(go, src=0)
     return n
-
-
-@dataclass
-class SlabTimings:
-    ms: float = 0.0
 
 
 class SlabModel:
